@@ -1,0 +1,189 @@
+/*
+ * sfm_b200.h -- C ABI of the B200-native SfM hot path.
+ *
+ * Drop-in boundary behind the three call sites of the reference
+ * (CaptainEven/SFM_OpenCV, OpenCV_SFM/NViewReconstuct.cpp):
+ *
+ *   match_features()            :873-913  (SIFT/L2 form: TwoViewReconstruct.cpp:156-194)
+ *   match_features_for_all()    :850-871
+ *   reconstruct()               :1117-1159 (cv::triangulatePoints + f32 de-homogenise)
+ *   ReprojectCost::operator()   :142-184  (residual blocks enumerated at :1187-1211)
+ *
+ * The reference has no FFI of its own (one C++ translation unit), so this
+ * header is what a maintainer binds instead of the OpenCV / Ceres calls; see
+ * INTEGRATION.md for the replacement bodies.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no torch / OpenCV types;
+ *   - every function returns 0 (SFM_OK) or a negative SFM_E_* code;
+ *     sfm_last_error(ctx) gives a human-readable message;
+ *   - pointers are HOST pointers unless the name ends in _dev; the library
+ *     owns all device memory; calls are synchronous on return;
+ *   - there is no CPU fallback: without a usable sm_100 device every compute
+ *     entry point fails with SFM_E_NO_DEVICE / SFM_E_CUDA.
+ *   - a context is bound to ONE device and is not thread-safe; use one
+ *     context per host thread / per GPU (pairs, points and observations are
+ *     independent, so callers shard them over contexts).
+ */
+#ifndef SFM_B200_H
+#define SFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SFM_API __attribute__((visibility("default")))
+#else
+#define SFM_API
+#endif
+
+/* error codes */
+enum {
+  SFM_OK = 0,
+  SFM_E_INVALID = -1,        /* null pointer, negative size, bad index ...        */
+  SFM_E_NO_DEVICE = -2,      /* no CUDA device / not compute capability 10.x      */
+  SFM_E_CUDA = -3,           /* a CUDA runtime / driver call failed               */
+  SFM_E_DIM = -4,            /* descriptor dimension is not 128                   */
+  SFM_E_NOT_INTEGRAL = -5,   /* float descriptor holds a non-integer value        */
+  SFM_E_RANGE = -6,          /* descriptor value outside 0..255, or row norm^2
+                                so large that float sqrt is no longer injective   */
+  SFM_E_TOO_FEW_TRAIN = -7,  /* a pair has fewer than 2 train descriptors: the
+                                reference would read knn_matches[i][1] out of
+                                bounds (NViewReconstuct.cpp:884)                  */
+  SFM_E_CAPACITY = -8,       /* output buffer too small; offsets[] hold the need  */
+  SFM_E_NOT_UPLOADED = -9,   /* sfm_match_pairs before sfm_upload_descriptors     */
+  SFM_E_NOMEM = -10
+};
+
+typedef struct sfm_ctx sfm_ctx;
+
+/* Layout-identical to cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}
+ * so a result buffer can be memcpy'd into a std::vector<cv::DMatch>. */
+typedef struct sfm_match_t {
+  int32_t queryIdx;
+  int32_t trainIdx;
+  int32_t imgIdx;   /* always 0, as cv::BFMatcher::knnMatch(query, train, ...) sets it */
+  float distance;   /* sqrtf((float)squared_distance), bit-exact with cv::NORM_L2       */
+} sfm_match_t;
+
+/* Raw k=2 result per query row (what knn_matches[i][0..1] hold at :877). */
+typedef struct sfm_knn2_t {
+  int32_t trainIdx0;
+  int32_t trainIdx1;
+  float distance0;
+  float distance1;
+} sfm_knn2_t;
+
+/* ---- context ------------------------------------------------------------------- */
+
+SFM_API int sfm_abi_version(void);
+/* Creates a context on CUDA device `device_id`. On failure returns NULL and, if
+ * err is non-null, stores the SFM_E_* code there. */
+SFM_API sfm_ctx* sfm_create(int device_id, int* err);
+SFM_API void sfm_destroy(sfm_ctx* ctx);
+SFM_API const char* sfm_last_error(const sfm_ctx* ctx);   /* ctx may be NULL: last create error */
+SFM_API const char* sfm_strerror(int code);
+
+/* Pinned host memory helpers (optional; any host pointer is accepted everywhere,
+ * pinned ones make the H2D/D2H copies asynchronous and faster). */
+SFM_API void* sfm_host_alloc(size_t bytes);
+SFM_API void sfm_host_free(void* p);
+
+/* ---- matching: replaces match_features / match_features_for_all ------------------ */
+
+/* Uploads the descriptor sets of n_img images (what extract_features() leaves in
+ * descriptor_for_all, NViewReconstuct.cpp:1366).  desc_f32[i] is a row-major
+ * n_desc[i] x 128 float matrix exactly as cv::SIFT produces (CV_32F, integer valued
+ * 0..255).  Values are validated on the device: SFM_E_NOT_INTEGRAL / SFM_E_RANGE.
+ * Replaces any previously uploaded bank. */
+SFM_API int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* desc_f32,
+                           const int32_t* n_desc, int dim);
+/* Same, for callers that already hold uint8 descriptors (4x less PCIe traffic). */
+SFM_API int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
+                              const int32_t* n_desc, int dim);
+
+/* For every pair p: knnMatch(desc[pair_q[p]], desc[pair_t[p]], k=2) with NORM_L2,
+ * then the reference's two filter passes (NViewReconstuct.cpp:880-908):
+ *   pass 1  min_dist = min{ d0 : !(d0 > ratio*d1) }           (double compare)
+ *   pass 2  keep knn[i][0] iff !(d0 > ratio*d1 || d0 > gate_mult*max(min_dist, dist_floor))
+ * Reference constants: ratio 0.6, dist_floor 10.0f, gate_mult 5.
+ * Kept matches of pair p are written, in ascending queryIdx, to
+ * out[offsets[p] .. offsets[p+1]).  offsets has n_pairs+1 entries and is always
+ * filled (also on SFM_E_CAPACITY, when out_cap < offsets[n_pairs]).
+ * knn_raw (nullable) receives sum_p n_desc[pair_q[p]] rows, pair after pair.
+ * min_dist (nullable) receives n_pairs floats (FLT_MAX when no row passes). */
+SFM_API int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, int n_pairs,
+                    double ratio, float dist_floor, float gate_mult,
+                    sfm_match_t* out, int64_t out_cap, int64_t* offsets,
+                    sfm_knn2_t* knn_raw, float* min_dist);
+
+/* Device-resident variant used to time the kernels without PCIe: runs the same
+ * kernels, keeps results on the device, returns only the total number of kept
+ * matches. kernel_ms (nullable) receives the CUDA-event time of the kNN kernel alone,
+ * total_ms (nullable) of the whole device pipeline. */
+SFM_API int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
+                             int n_pairs, double ratio, float dist_floor, float gate_mult,
+                             int64_t* total_matches, float* kernel_ms, float* total_ms);
+
+/* ---- triangulation: replaces cv::triangulatePoints + de-homogenise in reconstruct() -- */
+
+/* P: n_views row-major 3x4 float projection matrices, built by the caller exactly as
+ *    NViewReconstuct.cpp:1129-1143 does (float32 product fK*[R|T]).
+ * xy: view-major [n_views][n_pts][2] float image points (view v of point i at
+ *    xy[(v*n_pts+i)*2]); for n_views==2 these are the reference's pts2d_1, pts2d_2.
+ * X4 (nullable): [4][n_pts] float, the cv::triangulatePoints output layout (unit-norm
+ *    homogeneous columns; sign unspecified, as in OpenCV).
+ * xyz (nullable): [n_pts][3] double == std::vector<cv::Point3d>: float32 X/W widened to
+ *    double (NViewReconstuct.cpp:1151-1156).
+ * n_pts == 0 returns SFM_E_INVALID like the reference's -1 (:1122-1126). */
+SFM_API int sfm_triangulate_batch(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
+                          int64_t n_pts, float* X4, double* xyz);
+
+/* ---- reprojection residuals: replaces ReprojectCost::operator() evaluation --------- */
+
+/* intr = {fx, fy, cx, cy} (:1464-1471); ext[c] = {angle-axis(3), t(3)} (:1478-1486);
+ * pts[j] = 3 doubles (&pts3d[j].x, :1209); observation k belongs to camera cam_idx[k],
+ * point pt_idx[k], pixel obs_xy[2k..2k+1] (float KeyPoint::pt widened to double, :1199).
+ * resid (nullable): [n_obs][2] doubles, in the caller's observation order (the reference
+ * enumerates camera-major, :1187-1211).
+ * huber_cost (nullable): 0.5 * sum rho(|r|^2) with ceres::HuberLoss(huber_delta) (:1184);
+ * huber_delta <= 0 gives the plain 0.5*sum |r|^2. */
+SFM_API int sfm_reproject_residuals(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
+                            const double* pts, int64_t n_pts, const int32_t* cam_idx,
+                            const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                            double huber_delta, double* resid, double* huber_cost);
+
+/* ---- device-resident benchmarking hooks (inputs already in HBM) --------------------- */
+
+/* Stages the inputs of sfm_triangulate_batch / sfm_reproject_residuals on the device
+ * once, then runs the kernel `iters` times and reports the mean CUDA-event time per
+ * launch.  Results of the last launch are copied back when the output pointers are
+ * non-null.  Used by bench.py for the HBM roofline lines. */
+SFM_API int sfm_triangulate_batch_timed(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
+                                int64_t n_pts, float* X4, double* xyz, int iters,
+                                float* ms_per_launch);
+SFM_API int sfm_reproject_residuals_timed(sfm_ctx* ctx, const double intr[4], const double* ext,
+                                  int n_cam, const double* pts, int64_t n_pts,
+                                  const int32_t* cam_idx, const int32_t* pt_idx,
+                                  const float* obs_xy, int64_t n_obs, double huber_delta,
+                                  double* resid, double* huber_cost, int iters,
+                                  float* ms_per_launch);
+
+/* Bare tcgen05.mma.kind::i8 issue-rate probe: `iters` back-to-back 128x256x32 u8 MMAs
+ * per SM on all SMs, no epilogue.  Reports achieved tera-ops/s (2*M*N*K per MMA): the
+ * measured int8 tensor peak the matching roofline is quoted against. */
+SFM_API int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops);
+
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+SFM_API int64_t sfm_launch_count(const sfm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFM_B200_H */

@@ -1,0 +1,70 @@
+"""ctypes binding of include/sfm_b200.h. Fails loudly when the CUDA library is missing:
+there is no CPU fallback, and the product never touches the test oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfm_b200.so")
+
+SFM_OK = 0
+SFM_E_INVALID = -1
+SFM_E_NO_DEVICE = -2
+SFM_E_CUDA = -3
+SFM_E_DIM = -4
+SFM_E_NOT_INTEGRAL = -5
+SFM_E_RANGE = -6
+SFM_E_TOO_FEW_TRAIN = -7
+SFM_E_CAPACITY = -8
+SFM_E_NOT_UPLOADED = -9
+SFM_E_NOMEM = -10
+
+# every symbol include/sfm_b200.h declares: (restype, argtypes)
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+_pi, _pi64, _pf, _pd = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_double)
+SYMBOLS = {
+    "sfm_abi_version": (_i, []),
+    "sfm_create": (_vp, [_i, C.POINTER(C.c_int)]),
+    "sfm_destroy": (None, [_vp]),
+    "sfm_last_error": (C.c_char_p, [_vp]),
+    "sfm_strerror": (C.c_char_p, [_i]),
+    "sfm_host_alloc": (_vp, [C.c_size_t]),
+    "sfm_host_free": (None, [_vp]),
+    "sfm_upload_descriptors": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
+    "sfm_upload_descriptors_u8": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
+    "sfm_match_pairs": (_i, [_vp, _pi, _pi, _i, _d, _f, _f, _vp, _i64, _pi64, _vp, _pf]),
+    "sfm_match_pairs_resident": (_i, [_vp, _pi, _pi, _i, _d, _f, _f, _pi64, _pf, _pf]),
+    "sfm_triangulate_batch": (_i, [_vp, _pf, _pf, _i, _i64, _pf, _pd]),
+    "sfm_reproject_residuals": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _d, _pd, _pd]),
+    "sfm_triangulate_batch_timed": (_i, [_vp, _pf, _pf, _i, _i64, _pf, _pd, _i, _pf]),
+    "sfm_reproject_residuals_timed": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _d, _pd, _pd, _i, _pf]),
+    "sfm_probe_i8_peak": (_i, [_vp, _i, _pd]),
+    "sfm_launch_count": (_i64, [_vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libsfm_b200.so (built in-tree by sfm_opencv_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m sfm_opencv_b200.build` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class SfmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sfm_b200 error {code}: {msg}")
+        self.code = code

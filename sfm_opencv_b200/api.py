@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Names and argument meaning follow OpenCV_SFM/NViewReconstuct.cpp:
+    match_features(query, train)                 :873-913
+    match_features_for_all(descriptor_for_all)   :850-871
+    reconstruct(K, R1, T1, R2, T2, p1, p2)       :1117-1159
+    ReprojectCost / bundle_adjustment residuals  :142-184, :1187-1211
+All compute happens in libsfm_b200.so on the GPU; this module only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import SfmError
+
+RATIO = 0.6          # NViewReconstuct.cpp:884
+DIST_FLOOR = 10.0    # :901
+GATE_MULT = 5.0      # :901
+
+MATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"),
+                        ("distance", "<f4")])      # == cv::DMatch
+KNN_DTYPE = np.dtype([("trainIdx0", "<i4"), ("trainIdx1", "<i4"), ("distance0", "<f4"),
+                      ("distance1", "<f4")])
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+    """One sfm_ctx: one GPU, one host thread."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.load()
+        err = C.c_int(0)
+        self._h = self._lib.sfm_create(device, C.byref(err))
+        if not self._h:
+            raise SfmError(err.value, self._lib.sfm_last_error(None).decode())
+        self.device = device
+        self.n_desc: list[int] = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sfm_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SfmError(rc, self._lib.sfm_last_error(self._h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sfm_launch_count(self._h))
+
+    # ------------------------------------------------------------------ matching
+    def upload_descriptors(self, descriptor_for_all):
+        """descriptor_for_all: list of [n_i,128] arrays, float32 (as cv::SIFT gives) or uint8."""
+        descs = [np.ascontiguousarray(d) for d in descriptor_for_all]
+        if not descs:
+            raise SfmError(_capi.SFM_E_INVALID, "empty image list")
+        is_u8 = all(d.dtype == np.uint8 for d in descs)
+        if not is_u8:
+            descs = [np.ascontiguousarray(d, dtype=np.float32) for d in descs]
+        dims = {d.shape[1] for d in descs if d.ndim == 2}
+        dim = dims.pop() if len(dims) == 1 else -1
+        n = np.array([d.shape[0] for d in descs], np.int32)
+        ptrs = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs])
+        fn = self._lib.sfm_upload_descriptors_u8 if is_u8 else self._lib.sfm_upload_descriptors
+        self._check(fn(self._h, len(descs), ptrs, _ptr(n, C.c_int32), dim))
+        self.n_desc = [int(x) for x in n]
+
+    def match_pairs(self, pairs, ratio=RATIO, dist_floor=DIST_FLOOR, gate_mult=GATE_MULT,
+                    want_knn=False):
+        """pairs: iterable of (query_img, train_img). Returns (list of match arrays per pair,
+        min_dist[n_pairs], knn list or None)."""
+        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        n_pairs = pairs.shape[0]
+        pq = np.ascontiguousarray(pairs[:, 0])
+        pt = np.ascontiguousarray(pairs[:, 1])
+        if ((pq < 0) | (pq >= len(self.n_desc)) | (pt < 0) | (pt >= len(self.n_desc))).any():
+            raise SfmError(_capi.SFM_E_INVALID, "pair index out of range")
+        rows = int(sum(self.n_desc[q] for q in pq))
+        offsets = np.zeros(n_pairs + 1, np.int64)
+        min_dist = np.zeros(max(n_pairs, 1), np.float32)
+        out = np.zeros(max(rows, 1), MATCH_DTYPE)         # at most one match per query row
+        knn = np.zeros(max(rows, 1), KNN_DTYPE) if want_knn else None
+        self._check(self._lib.sfm_match_pairs(
+            self._h, _ptr(pq, C.c_int32), _ptr(pt, C.c_int32), n_pairs, ratio, dist_floor,
+            gate_mult, out.ctypes.data, rows, _ptr(offsets, C.c_int64),
+            knn.ctypes.data if want_knn else None, _ptr(min_dist, C.c_float)))
+        matches = [out[offsets[p]:offsets[p + 1]] for p in range(n_pairs)]
+        knn_list = None
+        if want_knn:
+            knn_list, r = [], 0
+            for q in pq:
+                knn_list.append(knn[r:r + self.n_desc[q]])
+                r += self.n_desc[q]
+        return matches, min_dist[:n_pairs], knn_list
+
+    def match_pairs_resident(self, pairs, ratio=RATIO, dist_floor=DIST_FLOOR,
+                             gate_mult=GATE_MULT):
+        """Device-resident timing hook: returns (total_matches, knn_kernel_ms, total_ms)."""
+        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        pq = np.ascontiguousarray(pairs[:, 0])
+        pt = np.ascontiguousarray(pairs[:, 1])
+        total = C.c_int64(0)
+        kms, tms = C.c_float(0), C.c_float(0)
+        self._check(self._lib.sfm_match_pairs_resident(
+            self._h, _ptr(pq, C.c_int32), _ptr(pt, C.c_int32), pairs.shape[0], ratio, dist_floor,
+            gate_mult, C.byref(total), C.byref(kms), C.byref(tms)))
+        return total.value, kms.value, tms.value
+
+    # ------------------------------------------------------------------ triangulation
+    def triangulate_batch(self, P, xy, want_X4=True, want_xyz=True, iters=0):
+        """P: [V,3,4] float32; xy: [V,N,2] float32. Returns (X4 [4,N] f32, xyz [N,3] f64[, ms])."""
+        P = np.ascontiguousarray(P, np.float32).reshape(-1, 3, 4)
+        xy = np.ascontiguousarray(xy, np.float32)
+        V = P.shape[0]
+        if xy.ndim != 3 or xy.shape[0] != V or xy.shape[2] != 2:
+            raise SfmError(_capi.SFM_E_INVALID, "xy must be [V,N,2]")
+        N = xy.shape[1]
+        X4 = np.empty((4, N), np.float32) if want_X4 else None
+        xyz = np.empty((N, 3), np.float64) if want_xyz else None
+        pX4 = _ptr(X4, C.c_float) if want_X4 and N else None
+        pxyz = _ptr(xyz, C.c_double) if want_xyz and N else None
+        if iters > 0:
+            ms = C.c_float(0)
+            self._check(self._lib.sfm_triangulate_batch_timed(
+                self._h, _ptr(P, C.c_float), _ptr(xy, C.c_float), V, N, pX4, pxyz, iters,
+                C.byref(ms)))
+            return X4, xyz, ms.value
+        self._check(self._lib.sfm_triangulate_batch(
+            self._h, _ptr(P, C.c_float), _ptr(xy, C.c_float), V, N, pX4, pxyz))
+        return X4, xyz
+
+    # ------------------------------------------------------------------ residuals
+    def reproject_residuals(self, intr, ext, pts, cam_idx, pt_idx, obs_xy, huber_delta=4.0,
+                            want_resid=True, want_cost=True, iters=0):
+        intr = np.ascontiguousarray(intr, np.float64).reshape(4)
+        ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 6)
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        cam_idx = np.ascontiguousarray(cam_idx, np.int32)
+        pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2)
+        n_obs = cam_idx.shape[0]
+        resid = np.empty((n_obs, 2), np.float64) if want_resid else None
+        cost = C.c_double(0)
+        args = [self._h, _ptr(intr, C.c_double), _ptr(ext, C.c_double), ext.shape[0],
+                _ptr(pts, C.c_double), pts.shape[0], _ptr(cam_idx, C.c_int32),
+                _ptr(pt_idx, C.c_int32), _ptr(obs_xy, C.c_float), n_obs, float(huber_delta),
+                _ptr(resid, C.c_double) if want_resid and n_obs else None,
+                C.byref(cost) if want_cost else None]
+        if iters > 0:
+            ms = C.c_float(0)
+            self._check(self._lib.sfm_reproject_residuals_timed(*args, iters, C.byref(ms)))
+            return resid, (cost.value if want_cost else None), ms.value
+        self._check(self._lib.sfm_reproject_residuals(*args))
+        return resid, (cost.value if want_cost else None)
+
+    def probe_i8_peak(self, iters: int = 2000) -> float:
+        tops = C.c_double(0)
+        self._check(self._lib.sfm_probe_i8_peak(self._h, iters, C.byref(tops)))
+        return tops.value
+
+
+# ---------------------------------------------------------------------- reference-shaped API
+
+def match_features(ctx: Context, query, train, **kw):
+    """match_features(query, train, matches), NViewReconstuct.cpp:873: returns the DMatch array."""
+    ctx.upload_descriptors([query, train])
+    m, _, _ = ctx.match_pairs([(0, 1)], **kw)
+    return m[0]
+
+
+def match_features_for_all(ctx: Context, descriptor_for_all, **kw):
+    """match_features_for_all, NViewReconstuct.cpp:850-871: consecutive pairs (i, i+1)."""
+    ctx.upload_descriptors(descriptor_for_all)
+    pairs = [(i, i + 1) for i in range(len(descriptor_for_all) - 1)]
+    m, _, _ = ctx.match_pairs(pairs, **kw)
+    return m
+
+
+def build_projection(K, R, T) -> np.ndarray:
+    """proj = fK * [R|T] as a float32 product, NViewReconstuct.cpp:1129-1143 (host glue)."""
+    RT = np.empty((3, 4), np.float32)
+    RT[:, :3] = np.asarray(R, np.float64).astype(np.float32)
+    RT[:, 3] = np.asarray(T, np.float64).reshape(3).astype(np.float32)
+    return (np.asarray(K, np.float64).astype(np.float32) @ RT).astype(np.float32)
+
+
+def reconstruct(ctx: Context, K, R1, T1, R2, T2, p1, p2):
+    """reconstruct(K,R1,T1,R2,T2,p1,p2,structure), NViewReconstuct.cpp:1117: returns structure
+    [N,3] float64 (Point3d); raises on empty input where the reference returns -1."""
+    p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    if p1.shape[0] == 0 or p2.shape[0] == 0:
+        raise SfmError(_capi.SFM_E_INVALID, "[Err]: empty 2d points.")
+    P = np.stack([build_projection(K, R1, T1), build_projection(K, R2, T2)])
+    _, xyz = ctx.triangulate_batch(P, np.stack([p1, p2]), want_X4=False)
+    return xyz

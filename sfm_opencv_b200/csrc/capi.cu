@@ -1,0 +1,585 @@
+// capi.cu -- the C ABI of include/sfm_b200.h: context, device memory, launches.
+// No CPU fallback: every compute entry point needs a live sm_100 device.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sfm_b200.h"
+#include "match_types.h"
+
+namespace sfm {
+// match_knn.cu
+cudaError_t launch_knn2(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const int32_t* ckey,
+                        const int32_t* norm, const PairDesc* pairs, const WorkItem* items,
+                        int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
+cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
+// match_finalize.cu
+cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
+                             int32_t* norm, int32_t* ckey, uint32_t* flags, cudaStream_t s);
+cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
+                          float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
+                          int64_t* offsets, cudaStream_t s);
+cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
+                                float dist_floor, float gate_mult, const float* min_dist,
+                                const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
+                                cudaStream_t s);
+cudaError_t launch_knn_to_float(const Knn2* knn, int64_t n, sfm_knn2_t* out, cudaStream_t s);
+// geometry.cu
+int geometry_grid(int64_t n, int n_sms);
+cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,
+                               float* X4, double* xyz, int n_sms, cudaStream_t s);
+cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
+cudaError_t launch_residuals(const double intr[4], const double* cam, const double* pts,
+                             const int32_t* cam_idx, const int32_t* pt_idx, const float* obs_xy,
+                             int64_t n_obs, double huber_delta, double* resid, double* block_cost,
+                             double* cost_out, int grid, cudaStream_t s);
+}  // namespace sfm
+
+using namespace sfm;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct sfm_ctx {
+  int device = 0;
+  int n_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  int64_t launches = 0;
+  EncodeTiledFn encode = nullptr;
+
+  // descriptor bank (padded rows)
+  DevBuf desc, norm, ckey, flags, stage;
+  std::vector<int32_t> img_n, img_row0;
+  int64_t bank_rows = 0;
+  bool bank_ready = false;
+  CUtensorMap tmap_a, tmap_b;
+
+  // matching scratch
+  DevBuf pairs, items, knn, counts, offsets, min_dist, out, knn_f;
+  // geometry scratch
+  DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char b__[512];                                                                     \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                      \
+      ctx->err = b__;                                                                    \
+      return e__ == cudaErrorMemoryAllocation ? SFM_E_NOMEM : SFM_E_CUDA;                \
+    }                                                                                    \
+  } while (0)
+
+static int fail(sfm_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+extern "C" {
+
+int sfm_abi_version(void) { return SFM_B200_ABI_VERSION; }
+
+const char* sfm_strerror(int code) {
+  switch (code) {
+    case SFM_OK: return "ok";
+    case SFM_E_INVALID: return "invalid argument";
+    case SFM_E_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case SFM_E_CUDA: return "CUDA error";
+    case SFM_E_DIM: return "descriptor dimension must be 128";
+    case SFM_E_NOT_INTEGRAL: return "descriptor holds a non-integer value";
+    case SFM_E_RANGE: return "descriptor value outside 0..255 or row norm too large";
+    case SFM_E_TOO_FEW_TRAIN: return "a pair has fewer than 2 train descriptors";
+    case SFM_E_CAPACITY: return "output buffer too small";
+    case SFM_E_NOT_UPLOADED: return "descriptors not uploaded";
+    case SFM_E_NOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+const char* sfm_last_error(const sfm_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+sfm_ctx* sfm_create(int device_id, int* err) {
+  auto bail = [&](int code, const std::string& msg) -> sfm_ctx* {
+    g_create_error = msg;
+    if (err) *err = code;
+    return nullptr;
+  };
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return bail(SFM_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= n_dev) return bail(SFM_E_INVALID, "device id out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess)
+    return bail(SFM_E_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return bail(SFM_E_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
+  if (cudaSetDevice(device_id) != cudaSuccess) return bail(SFM_E_CUDA, "cudaSetDevice failed");
+  sfm_ctx* ctx = new sfm_ctx();
+  ctx->device = device_id;
+  ctx->n_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return bail(SFM_E_CUDA, "cudaStreamCreate failed");
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      fn == nullptr) {
+    sfm_destroy(ctx);
+    return bail(SFM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (err) *err = SFM_OK;
+  return ctx;
+}
+
+void sfm_destroy(sfm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->flags, &ctx->stage, &ctx->pairs,
+                    &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
+                    &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
+                    &ctx->gres, &ctx->gbc, &ctx->gcost};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* sfm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void sfm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int64_t sfm_launch_count(const sfm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ----------------------------------------------------------------------------- upload
+static int make_tmap(sfm_ctx* ctx, CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), rows};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kDim), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    ctx->err = b;
+    return SFM_E_CUDA;
+  }
+  return SFM_OK;
+}
+
+static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const int32_t* n_desc,
+                         int dim, bool f32) {
+  if (!ctx) return SFM_E_INVALID;
+  if (n_img <= 0 || !desc || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
+  if (dim != kDim) return fail(ctx, SFM_E_DIM, "descriptor dimension must be 128 (SIFT)");
+  CK(cudaSetDevice(ctx->device));
+  ctx->bank_ready = false;
+  ctx->img_n.assign(n_desc, n_desc + n_img);
+  ctx->img_row0.resize(n_img);
+  int64_t rows = 0;
+  int32_t max_n = 0;
+  for (int i = 0; i < n_img; ++i) {
+    if (n_desc[i] < 0 || (n_desc[i] > 0 && !desc[i]))
+      return fail(ctx, SFM_E_INVALID, "negative count or null descriptor pointer");
+    ctx->img_row0[i] = static_cast<int32_t>(rows);
+    rows += (static_cast<int64_t>(n_desc[i]) + kRowPad - 1) / kRowPad * kRowPad;
+    if (n_desc[i] > max_n) max_n = n_desc[i];
+    if (rows > INT32_MAX - kRowPad) return fail(ctx, SFM_E_INVALID, "descriptor bank too large");
+  }
+  if (rows == 0) rows = kRowPad;
+  ctx->bank_rows = rows;
+  CK(ctx->desc.ensure(static_cast<size_t>(rows) * kDim));
+  CK(ctx->norm.ensure(static_cast<size_t>(rows) * 4));
+  CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
+  CK(ctx->flags.ensure(4));
+  const size_t elt = f32 ? 4 : 1;
+  const size_t img_bytes = static_cast<size_t>(max_n) * kDim * elt;
+  CK(ctx->stage.ensure(2 * img_bytes + 512));
+  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, ctx->stream));
+  CK(cudaMemsetAsync(ctx->flags.p, 0, 4, ctx->stream));
+  for (int i = 0; i < n_img; ++i) {
+    // alternate staging halves; copies and pack kernels are ordered by the single stream
+    uint8_t* st = ctx->stage.as<uint8_t>() + (i & 1) * ((img_bytes + 255) / 256 * 256);
+    const size_t bytes = static_cast<size_t>(n_desc[i]) * kDim * elt;
+    if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_pack_rows(f32, st, n_desc[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
+                        ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(),
+                        ctx->flags.as<uint32_t>(), ctx->stream));
+    ctx->launches += 2;
+  }
+  uint32_t flags = 0;
+  CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (flags & 2u) return fail(ctx, SFM_E_RANGE, "descriptor value outside 0..255");
+  if (flags & 1u) return fail(ctx, SFM_E_NOT_INTEGRAL, "descriptor holds a non-integer value");
+  if (flags & 4u)
+    return fail(ctx, SFM_E_RANGE,
+                "descriptor row norm^2 >= 2^21: float sqrt no longer injective on the distances");
+  int rc = make_tmap(ctx, &ctx->tmap_a, ctx->desc.p, static_cast<uint64_t>(rows), kTileM);
+  if (rc) return rc;
+  rc = make_tmap(ctx, &ctx->tmap_b, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
+  if (rc) return rc;
+  ctx->bank_ready = true;
+  return SFM_OK;
+}
+
+int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* desc_f32,
+                           const int32_t* n_desc, int dim) {
+  return upload_common(ctx, n_img, reinterpret_cast<const void* const*>(desc_f32), n_desc, dim,
+                       true);
+}
+
+int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
+                              const int32_t* n_desc, int dim) {
+  return upload_common(ctx, n_img, reinterpret_cast<const void* const*>(desc_u8), n_desc, dim,
+                       false);
+}
+
+// ----------------------------------------------------------------------------- matching
+// Builds the pair / work-item tables, runs kNN + filter passes, leaves results on the device.
+static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, int n_pairs,
+                        double ratio, float dist_floor, float gate_mult, int64_t* total_rows,
+                        bool time_it) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!ctx->bank_ready) return fail(ctx, SFM_E_NOT_UPLOADED, "call sfm_upload_descriptors first");
+  if (n_pairs < 0 || (n_pairs > 0 && (!pair_q || !pair_t)))
+    return fail(ctx, SFM_E_INVALID, "null pair list");
+  CK(cudaSetDevice(ctx->device));
+  const int n_img = static_cast<int>(ctx->img_n.size());
+  std::vector<PairDesc> pairs(n_pairs);
+  std::vector<WorkItem> items;
+  int64_t rows = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const int q = pair_q[p], t = pair_t[p];
+    if (q < 0 || q >= n_img || t < 0 || t >= n_img)
+      return fail(ctx, SFM_E_INVALID, "pair index out of range");
+    if (ctx->img_n[t] < 2 && ctx->img_n[q] > 0)
+      return fail(ctx, SFM_E_TOO_FEW_TRAIN,
+                  "train image has fewer than 2 descriptors (reference reads knn[i][1])");
+    PairDesc& pd = pairs[p];
+    pd.q_row0 = ctx->img_row0[q];
+    pd.t_row0 = ctx->img_row0[t];
+    pd.nq = ctx->img_n[q];
+    pd.nt = ctx->img_n[t];
+    pd.knn_off = rows;
+    rows += pd.nq;
+    const int mt = (pd.nq + kTileM - 1) / kTileM;
+    for (int m = 0; m < mt; ++m) items.push_back(WorkItem{p, m});
+  }
+  *total_rows = rows;
+  if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many tiles");
+  CK(ctx->pairs.ensure(sizeof(PairDesc) * (n_pairs + 1)));
+  CK(ctx->items.ensure(sizeof(WorkItem) * (items.size() + 1)));
+  CK(ctx->knn.ensure(sizeof(Knn2) * (rows + 1)));
+  CK(ctx->counts.ensure(4 * (n_pairs + 1)));
+  CK(ctx->offsets.ensure(8 * (n_pairs + 1)));
+  CK(ctx->min_dist.ensure(4 * (n_pairs + 1)));
+  if (n_pairs)
+    CK(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), sizeof(PairDesc) * n_pairs,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  if (!items.empty())
+    CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(WorkItem) * items.size(),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(launch_knn2(ctx->tmap_a, ctx->tmap_b, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
+                 ctx->pairs.as<PairDesc>(), ctx->items.as<WorkItem>(),
+                 static_cast<int>(items.size()), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+  if (!items.empty()) ctx->launches += 1;
+  if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
+                   gate_mult, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
+                   ctx->offsets.as<int64_t>(), ctx->stream));
+  ctx->launches += (n_pairs > 0 ? 2 : 1);
+  return SFM_OK;
+}
+
+int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, int n_pairs,
+                    double ratio, float dist_floor, float gate_mult, sfm_match_t* out,
+                    int64_t out_cap, int64_t* offsets, sfm_knn2_t* knn_raw, float* min_dist) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!offsets) return fail(ctx, SFM_E_INVALID, "offsets must not be null");
+  if (out_cap < 0 || (out_cap > 0 && !out)) return fail(ctx, SFM_E_INVALID, "bad output buffer");
+  int64_t rows = 0;
+  int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, false);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(offsets, ctx->offsets.p, 8 * (n_pairs + 1), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  if (min_dist && n_pairs)
+    CK(cudaMemcpyAsync(min_dist, ctx->min_dist.p, 4 * n_pairs, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  if (knn_raw && rows) {
+    CK(ctx->knn_f.ensure(sizeof(sfm_knn2_t) * rows));
+    CK(launch_knn_to_float(ctx->knn.as<Knn2>(), rows, ctx->knn_f.as<sfm_knn2_t>(), ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(knn_raw, ctx->knn_f.p, sizeof(sfm_knn2_t) * rows, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int64_t total = offsets[n_pairs];
+  if (total > out_cap) {
+    ctx->err = "output capacity too small; offsets[n_pairs] holds the required size";
+    return SFM_E_CAPACITY;
+  }
+  if (total > 0) {
+    CK(ctx->out.ensure(sizeof(sfm_match_t) * total));
+    CK(launch_filter_write(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio,
+                           dist_floor, gate_mult, ctx->min_dist.as<float>(),
+                           ctx->offsets.as<int64_t>(), ctx->out.as<sfm_match_t>(), total,
+                           ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(out, ctx->out.p, sizeof(sfm_match_t) * total, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFM_OK;
+}
+
+int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
+                             int n_pairs, double ratio, float dist_floor, float gate_mult,
+                             int64_t* total_matches, float* kernel_ms, float* total_ms) {
+  if (!ctx) return SFM_E_INVALID;
+  int64_t rows = 0;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, true);
+  if (rc) return rc;
+  int64_t total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->offsets.as<int64_t>() + n_pairs, 8, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total > 0) {
+    CK(ctx->out.ensure(sizeof(sfm_match_t) * total));
+    CK(launch_filter_write(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio,
+                           dist_floor, gate_mult, ctx->min_dist.as<float>(),
+                           ctx->offsets.as<int64_t>(), ctx->out.as<sfm_match_t>(), total,
+                           ctx->stream));
+    ctx->launches += 1;
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total_matches) *total_matches = total;
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev[0], ctx->ev[1]));
+  if (total_ms) CK(cudaEventElapsedTime(total_ms, ctx->ev[2], ctx->ev[3]));
+  return SFM_OK;
+}
+
+// ----------------------------------------------------------------------------- triangulation
+static int triangulate_common(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
+                              int64_t n_pts, float* X4, double* xyz, int iters,
+                              float* ms_per_launch) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!P || !xy || n_views < 2) return fail(ctx, SFM_E_INVALID, "need P, xy and >= 2 views");
+  if (n_pts <= 0) return fail(ctx, SFM_E_INVALID, "[Err]: empty 2d points.");   // :1122-1126
+  CK(cudaSetDevice(ctx->device));
+  const size_t nP = sizeof(float) * 12 * n_views;
+  const size_t nxy = sizeof(float) * 2 * n_views * n_pts;
+  CK(ctx->gP.ensure(nP));
+  CK(ctx->gxy.ensure(nxy));
+  CK(ctx->gX4.ensure(sizeof(float) * 4 * n_pts));
+  CK(ctx->gxyz.ensure(sizeof(double) * 3 * n_pts));
+  CK(cudaMemcpyAsync(ctx->gP.p, P, nP, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gxy.p, xy, nxy, cudaMemcpyHostToDevice, ctx->stream));
+  float* dX4 = (X4 || iters > 0) ? ctx->gX4.as<float>() : nullptr;
+  double* dxyz = (xyz || iters > 0) ? ctx->gxyz.as<double>() : nullptr;
+  const int reps = iters > 0 ? iters : 1;
+  if (iters > 0) {   // one untimed warm-up launch
+    CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
+                          ctx->n_sms, ctx->stream));
+    ctx->launches += 1;
+  }
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int r = 0; r < reps; ++r) {
+    CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
+                          ctx->n_sms, ctx->stream));
+    ctx->launches += 1;
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (X4)
+    CK(cudaMemcpyAsync(X4, ctx->gX4.p, sizeof(float) * 4 * n_pts, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  if (xyz)
+    CK(cudaMemcpyAsync(xyz, ctx->gxyz.p, sizeof(double) * 3 * n_pts, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ms_per_launch) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    *ms_per_launch = ms / reps;
+  }
+  return SFM_OK;
+}
+
+int sfm_triangulate_batch(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
+                          int64_t n_pts, float* X4, double* xyz) {
+  return triangulate_common(ctx, P, xy, n_views, n_pts, X4, xyz, 0, nullptr);
+}
+
+int sfm_triangulate_batch_timed(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
+                                int64_t n_pts, float* X4, double* xyz, int iters,
+                                float* ms_per_launch) {
+  if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
+  return triangulate_common(ctx, P, xy, n_views, n_pts, X4, xyz, iters, ms_per_launch);
+}
+
+// ----------------------------------------------------------------------------- residuals
+static int residual_common(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
+                           const double* pts, int64_t n_pts, const int32_t* cam_idx,
+                           const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                           double huber_delta, double* resid, double* huber_cost, int iters,
+                           float* ms_per_launch) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!intr || !ext || !pts || n_cam <= 0 || n_pts <= 0)
+    return fail(ctx, SFM_E_INVALID, "null camera / point tables");
+  if (n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)))
+    return fail(ctx, SFM_E_INVALID, "null observation arrays");
+  for (int64_t k = 0; k < n_obs; ++k) {
+    if (cam_idx[k] < 0 || cam_idx[k] >= n_cam || pt_idx[k] < 0 || pt_idx[k] >= n_pts)
+      return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (n_obs == 0) {
+    if (huber_cost) *huber_cost = 0.0;
+    return SFM_OK;
+  }
+  const int grid = geometry_grid(n_obs, ctx->n_sms);
+  CK(ctx->gext.ensure(sizeof(double) * 6 * n_cam));
+  CK(ctx->gcam.ensure(sizeof(double) * 12 * n_cam));
+  CK(ctx->gpts.ensure(sizeof(double) * 3 * n_pts));
+  CK(ctx->gci.ensure(4 * n_obs));
+  CK(ctx->gpi.ensure(4 * n_obs));
+  CK(ctx->gobs.ensure(8 * n_obs));
+  CK(ctx->gres.ensure(16 * n_obs));
+  CK(ctx->gbc.ensure(8 * grid));
+  CK(ctx->gcost.ensure(8));
+  CK(cudaMemcpyAsync(ctx->gext.p, ext, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gpts.p, pts, sizeof(double) * 3 * n_pts, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gci.p, cam_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gpi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gobs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_camera_table(ctx->gext.as<double>(), n_cam, ctx->gcam.as<double>(), ctx->stream));
+  ctx->launches += 1;
+  double* dres = (resid || iters > 0) ? ctx->gres.as<double>() : nullptr;
+  double* dbc = huber_cost ? ctx->gbc.as<double>() : nullptr;
+  const int reps = iters > 0 ? iters : 1;
+  const int n_launch = huber_cost ? 2 : 1;
+  if (iters > 0) {
+    CK(launch_residuals(intr, ctx->gcam.as<double>(), ctx->gpts.as<double>(),
+                        ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), ctx->gobs.as<float>(),
+                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream));
+    ctx->launches += n_launch;
+  }
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int r = 0; r < reps; ++r) {
+    CK(launch_residuals(intr, ctx->gcam.as<double>(), ctx->gpts.as<double>(),
+                        ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), ctx->gobs.as<float>(),
+                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream));
+    ctx->launches += n_launch;
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (resid)
+    CK(cudaMemcpyAsync(resid, ctx->gres.p, 16 * n_obs, cudaMemcpyDeviceToHost, ctx->stream));
+  if (huber_cost)
+    CK(cudaMemcpyAsync(huber_cost, ctx->gcost.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ms_per_launch) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    *ms_per_launch = ms / reps;
+  }
+  return SFM_OK;
+}
+
+int sfm_reproject_residuals(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
+                            const double* pts, int64_t n_pts, const int32_t* cam_idx,
+                            const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                            double huber_delta, double* resid, double* huber_cost) {
+  return residual_common(ctx, intr, ext, n_cam, pts, n_pts, cam_idx, pt_idx, obs_xy, n_obs,
+                         huber_delta, resid, huber_cost, 0, nullptr);
+}
+
+int sfm_reproject_residuals_timed(sfm_ctx* ctx, const double intr[4], const double* ext,
+                                  int n_cam, const double* pts, int64_t n_pts,
+                                  const int32_t* cam_idx, const int32_t* pt_idx,
+                                  const float* obs_xy, int64_t n_obs, double huber_delta,
+                                  double* resid, double* huber_cost, int iters,
+                                  float* ms_per_launch) {
+  if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
+  return residual_common(ctx, intr, ext, n_cam, pts, n_pts, cam_idx, pt_idx, obs_xy, n_obs,
+                         huber_delta, resid, huber_cost, iters, ms_per_launch);
+}
+
+// ----------------------------------------------------------------------------- probe
+int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops) {
+  if (!ctx) return SFM_E_INVALID;
+  if (iters <= 0 || !tops) return fail(ctx, SFM_E_INVALID, "bad probe arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_i8_peak(iters, ctx->n_sms, ctx->stream));   // warm-up
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(launch_i8_peak(iters, ctx->n_sms, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 2;
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  const double ops = 2.0 * kTileM * kTileN * 32.0 * 4.0 * iters * ctx->n_sms;
+  *tops = ops / (ms * 1e-3) / 1e12;
+  return SFM_OK;
+}
+
+}  // extern "C"

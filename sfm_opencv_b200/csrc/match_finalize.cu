@@ -1,0 +1,264 @@
+// match_finalize.cu -- descriptor packing and the reference's two filter passes on the device.
+//
+//  pack_*            : what sfm_upload_descriptors does with descriptor_for_all[i]
+//                      (CV_32F SIFT rows -> validated u8 rows + |row|^2 + packed column keys)
+//  filter_count/write: match_features passes 1 and 2, OpenCV_SFM/NViewReconstuct.cpp:880-908,
+//                      one block per image pair, kept matches in ascending queryIdx.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/sfm_b200.h"
+#include "match_types.h"
+
+namespace sfm {
+
+// flags accumulated by the pack kernels
+constexpr uint32_t kFlagNotIntegral = 1u;
+constexpr uint32_t kFlagRange = 2u;
+constexpr uint32_t kFlagNorm = 4u;
+// float sqrt is injective on integers below 2^22: require |q|^2 + |t|^2 < 2^22
+constexpr int kMaxNorm = (1 << 21) - 1;
+
+// One warp per descriptor row. src = float rows (is_f32) or u8 rows of ONE image;
+// dst rows are in padded bank coordinates starting at row0.
+template <bool kF32>
+__global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
+                                 uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
+                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  uint32_t packed;
+  uint32_t bad = 0;
+  if constexpr (kF32) {
+    const float4 v = reinterpret_cast<const float4*>(src)[static_cast<size_t>(r) * 32 + lane];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = f[k];
+      if (!(x >= 0.0f && x <= 255.0f)) bad |= kFlagRange;        // also catches NaN
+      else if (x != rintf(x)) bad |= kFlagNotIntegral;
+      const uint32_t b = static_cast<uint32_t>(fminf(fmaxf(x, 0.0f), 255.0f));
+      packed |= b << (8 * k);
+    }
+  } else {
+    packed = reinterpret_cast<const uint32_t*>(src)[static_cast<size_t>(r) * 32 + lane];
+  }
+  reinterpret_cast<uint32_t*>(desc)[static_cast<size_t>(row0 + r) * 32 + lane] = packed;
+  int s = __dp4a(packed, packed, 0u);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (s > kMaxNorm) bad |= kFlagNorm;
+  if (lane == 0) {
+    norm[row0 + r] = s;
+    ckey[row0 + r] = (s << 8) | (r & 255);
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if (bad && lane == 0) atomicOr(flags, bad);
+}
+
+// Padding rows [n, n_pad) of an image: zero descriptor (bank is memset), sentinel norm.
+__global__ void pad_rows_kernel(int n, int n_pad, int row0, int32_t* __restrict__ norm,
+                                int32_t* __restrict__ ckey) {
+  const int r = n + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_pad) {
+    norm[row0 + r] = kNormPad;
+    ckey[row0 + r] = (kNormPad << 8) | (r & 255);
+  }
+}
+
+// ------------------------------------------------------------------------------- filter
+__device__ __forceinline__ bool ratio_fails(float d0, float d1, double ratio) {
+  // `knn[i][0].distance > 0.6 * knn[i][1].distance`: float promoted to double (:884, :900)
+  return static_cast<double>(d0) > ratio * static_cast<double>(d1);
+}
+
+// Pass 1 + count of pass 2. One block per pair.
+__global__ void __launch_bounds__(256)
+filter_count_kernel(const Knn2* __restrict__ knn, const PairDesc* __restrict__ pairs, double ratio,
+                    float dist_floor, float gate_mult, float* __restrict__ min_dist,
+                    int32_t* __restrict__ counts) {
+  __shared__ uint32_t s_min;
+  __shared__ int s_cnt;
+  const PairDesc pd = pairs[blockIdx.x];
+  const Knn2* k = knn + pd.knn_off;
+  if (threadIdx.x == 0) {
+    s_min = __float_as_uint(FLT_MAX);
+    s_cnt = 0;
+  }
+  __syncthreads();
+  uint32_t lmin = __float_as_uint(FLT_MAX);
+  for (int i = threadIdx.x; i < pd.nq; i += blockDim.x) {
+    const int4 v = *reinterpret_cast<const int4*>(&k[i]);
+    const float d0 = __fsqrt_rn(static_cast<float>(v.z));
+    const float d1 = __fsqrt_rn(static_cast<float>(v.w));
+    if (!ratio_fails(d0, d1, ratio)) lmin = min(lmin, __float_as_uint(d0));  // d0 >= 0
+  }
+  lmin = __reduce_min_sync(0xffffffffu, lmin);
+  if ((threadIdx.x & 31) == 0) atomicMin(&s_min, lmin);
+  __syncthreads();
+  const float md = __uint_as_float(s_min);
+  const float gate = gate_mult * fmaxf(md, dist_floor);   // 5 * max(min_dist, 10.0f), float
+  int c = 0;
+  for (int i = threadIdx.x; i < pd.nq; i += blockDim.x) {
+    const int4 v = *reinterpret_cast<const int4*>(&k[i]);
+    const float d0 = __fsqrt_rn(static_cast<float>(v.z));
+    const float d1 = __fsqrt_rn(static_cast<float>(v.w));
+    c += !(ratio_fails(d0, d1, ratio) || d0 > gate);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    min_dist[blockIdx.x] = md;
+    counts[blockIdx.x] = s_cnt;
+  }
+}
+
+// Exclusive scan of counts -> offsets[n+1] (int64). Single block; n is at most ~1e6.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int32_t* __restrict__ counts, int n, int64_t* __restrict__ offsets) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int64_t v = i < n ? counts[i] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int64_t incl = x + (warp ? s_warp[warp - 1] : 0) + s_carry;
+    if (i < n) offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = s_carry;
+}
+
+// Pass 2: ordered compaction of the kept matches of each pair.
+__global__ void __launch_bounds__(256)
+filter_write_kernel(const Knn2* __restrict__ knn, const PairDesc* __restrict__ pairs, double ratio,
+                    float dist_floor, float gate_mult, const float* __restrict__ min_dist,
+                    const int64_t* __restrict__ offsets, sfm_match_t* __restrict__ out,
+                    int64_t out_cap) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const PairDesc pd = pairs[blockIdx.x];
+  const Knn2* k = knn + pd.knn_off;
+  const int64_t off = offsets[blockIdx.x];
+  const float gate = gate_mult * fmaxf(min_dist[blockIdx.x], dist_floor);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < pd.nq; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    bool keep = false;
+    int4 v = make_int4(0, 0, 0, 0);
+    float d0 = 0.f;
+    if (i < pd.nq) {
+      v = *reinterpret_cast<const int4*>(&k[i]);
+      d0 = __fsqrt_rn(static_cast<float>(v.z));
+      const float d1 = __fsqrt_rn(static_cast<float>(v.w));
+      keep = !(ratio_fails(d0, d1, ratio) || d0 > gate);
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int rank = before + __popc(ballot & ((1u << lane) - 1u));
+    if (keep && off + rank < out_cap) {
+      sfm_match_t m;
+      m.queryIdx = i;
+      m.trainIdx = v.x;
+      m.imgIdx = 0;
+      m.distance = d0;
+      *reinterpret_cast<int4*>(&out[off + rank]) = *reinterpret_cast<int4*>(&m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// Knn2 (integer squared distances) -> sfm_knn2_t (float distances, as DMatch::distance).
+__global__ void knn_to_float_kernel(const Knn2* __restrict__ knn, int64_t n,
+                                    sfm_knn2_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 v = *reinterpret_cast<const int4*>(&knn[i]);
+  int4 o;
+  o.x = v.x;
+  o.y = v.y;
+  o.z = __float_as_int(__fsqrt_rn(static_cast<float>(v.z)));
+  o.w = __float_as_int(__fsqrt_rn(static_cast<float>(v.w)));
+  *reinterpret_cast<int4*>(&out[i]) = o;
+}
+
+// ------------------------------------------------------------------------------- launchers
+cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
+                             int32_t* norm, int32_t* ckey, uint32_t* flags, cudaStream_t s) {
+  if (n > 0) {
+    const int warps = 8;
+    const int grid = (n + warps - 1) / warps;
+    if (f32)
+      pack_rows_kernel<true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
+    else
+      pack_rows_kernel<false><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
+  }
+  const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
+  if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 255) / 256, 256, 0, s>>>(n, n_pad, row0, norm, ckey);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
+                          float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
+                          int64_t* offsets, cudaStream_t s) {
+  if (n_pairs > 0)
+    filter_count_kernel<<<n_pairs, 256, 0, s>>>(knn, pairs, ratio, dist_floor, gate_mult, min_dist,
+                                                counts);
+  scan_counts_kernel<<<1, 1024, 0, s>>>(counts, n_pairs, offsets);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
+                                float dist_floor, float gate_mult, const float* min_dist,
+                                const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
+                                cudaStream_t s) {
+  if (n_pairs > 0)
+    filter_write_kernel<<<n_pairs, 256, 0, s>>>(knn, pairs, ratio, dist_floor, gate_mult, min_dist,
+                                                offsets, out, out_cap);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_to_float(const Knn2* knn, int64_t n, sfm_knn2_t* out, cudaStream_t s) {
+  if (n > 0)
+    knn_to_float_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(knn, n, out);
+  return cudaGetLastError();
+}
+
+}  // namespace sfm

@@ -1,0 +1,65 @@
+"""Generates the committed golden fixtures from the reference's bundled datasets.
+
+Run HERE (container with /root/reference and cv2 4.13); the fixtures travel, this script's
+inputs do not.  For each dataset: SIFT_create(0,3,0.04,10) descriptors (the parameters of
+OpenCV_SFM/TwoViewReconstruct.cpp:112), then for every consecutive pair
+(NViewReconstuct.cpp:857-870) the reference's own library call
+cv2.BFMatcher(NORM_L2).knnMatch(k=2) and the filter of NViewReconstuct.cpp:880-908.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import glob
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import matching as M  # noqa: E402
+
+REF = "/root/reference/dataset"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sift_dataset(name: str):
+    files = sorted(glob.glob(os.path.join(REF, name, "*.[jJ][pP][gG]")))
+    sift = cv2.SIFT_create(0, 3, 0.04, 10)
+    descs, kps = [], []
+    for f in files:
+        img = cv2.imread(f)
+        kp = sift.detect(img, None)
+        kp, d = sift.compute(img, kp)
+        descs.append(M.as_u8(d))
+        kps.append(np.array([k.pt for k in kp], np.float32))
+        print(name, os.path.basename(f), d.shape, flush=True)
+    return files, descs, kps
+
+
+def main():
+    for name in ("crazyhorse", "desktop"):
+        files, descs, kps = sift_dataset(name)
+        out = {"n_img": np.int32(len(descs))}
+        for i, (d, k) in enumerate(zip(descs, kps)):
+            out[f"desc_{i}"] = d
+            out[f"kp_{i}"] = k
+        for i in range(len(descs) - 1):
+            q = descs[i].astype(np.float32)
+            t = descs[i + 1].astype(np.float32)
+            dist, idx = M.knn2_cv(q, t)                      # the reference's library call
+            m, d0, md = M.filter_matches(dist, idx)
+            out[f"knn_dist_{i}"] = dist
+            out[f"knn_idx_{i}"] = idx
+            out[f"match_{i}"] = m
+            out[f"match_dist_{i}"] = d0
+            out[f"min_dist_{i}"] = np.float32(md)
+            ties = int((dist[:, 0] == dist[:, 1]).sum())
+            print(name, "pair", i, "matches", len(m), "min_dist", md, "tie rows", ties, flush=True)
+        np.savez_compressed(os.path.join(OUT, f"{name}_sift.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

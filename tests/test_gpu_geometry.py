@@ -1,0 +1,133 @@
+"""GPU parity (through the C ABI): sfm_triangulate_batch / sfm_reproject_residuals vs the
+CPU oracle.  Tolerance (BASELINE.json north_star): 1e-5 relative."""
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5      # per-point ||dX||/||X||, and residuals relative to the pixel scale below
+
+
+def test_two_view_vs_cv2(ctx):
+    sc = synth.scene(20000, 2, seed=7)
+    X4, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+    cv = G.triangulate_cv(sc["P"][0], sc["P"][1], sc["xy"][0], sc["xy"][1])
+    assert X4.dtype == np.float32 and X4.shape == cv.shape
+    assert np.allclose(np.linalg.norm(X4.astype(np.float64), axis=0), 1.0, atol=1e-6)
+    ref = G.dehomogenize(cv)
+    assert G.point_rel_err(xyz, ref).max() < REL_TOL
+    # xyz is the float32 quotient widened to double, exactly as the reference stores it
+    assert np.array_equal(xyz, G.dehomogenize(X4))
+    # homogeneous vectors agree up to the sign OpenCV leaves unspecified
+    s = np.sign((X4 * cv).sum(0))
+    assert np.abs(X4 * s - cv).max() < 1e-6
+
+
+@pytest.mark.parametrize("V", [2, 3, 4, 8])
+def test_n_view_vs_svd(ctx, V):
+    sc = synth.scene(8000, V, seed=11 + V)
+    _, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+    ref = G.dehomogenize(G.triangulate_svd(sc["P"], sc["xy"]))
+    assert G.point_rel_err(xyz, ref).max() < REL_TOL
+
+
+def test_noiseless_points_are_recovered(ctx):
+    sc = synth.scene(5000, 3, seed=5, noise_px=0.0)
+    _, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+    assert G.point_rel_err(xyz, sc["X"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("n", [1, 31, 257, 1000])
+def test_ragged_point_counts(ctx, n):
+    sc = synth.scene(n, 2, seed=n)
+    _, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+    ref, _ = G.reconstruct(G.K_REFERENCE, np.eye(3), np.zeros(3), *_rt(sc, 1),
+                           sc["xy"][0], sc["xy"][1])
+    assert xyz.shape == (n, 3) and G.point_rel_err(xyz, ref).max() < REL_TOL
+
+
+def _rt(sc, v):
+    import cv2
+    R, _ = cv2.Rodrigues(sc["ext"][v, :3].reshape(3, 1))
+    return R, sc["ext"][v, 3:]
+
+
+def test_reconstruct_api_and_empty(ctx):
+    import sfm_opencv_b200 as sfm
+    sc = synth.scene(777, 2, seed=3)
+    R, T = _rt(sc, 1)
+    xyz = sfm.reconstruct(ctx, G.K_REFERENCE, np.eye(3), np.zeros(3), R, T, sc["xy"][0], sc["xy"][1])
+    ref, _ = G.reconstruct(G.K_REFERENCE, np.eye(3), np.zeros(3), R, T, sc["xy"][0], sc["xy"][1])
+    assert G.point_rel_err(xyz, ref).max() < REL_TOL
+    with pytest.raises(sfm.SfmError):           # reference: "[Err]: empty 2d points." -> -1
+        sfm.reconstruct(ctx, G.K_REFERENCE, np.eye(3), np.zeros(3), R, T, np.zeros((0, 2)), np.zeros((0, 2)))
+
+
+def test_golden_desktop_two_view_points(ctx, golden):
+    """Matches of desktop pair 0 -> E/pose by cv2 (host glue, out of scope) -> triangulate on
+    the GPU vs cv2.triangulatePoints on the same inliers."""
+    import cv2
+    g = golden("desktop")
+    m = g["match_0"]
+    p1 = g["kp_0"][m[:, 0]]; p2 = g["kp_1"][m[:, 1]]
+    K = G.K_REFERENCE
+    f = 0.5 * (K[0, 0] + K[1, 1]); pp = (K[0, 2], K[1, 2])
+    cv2.setRNGSeed(0)
+    E, mask = cv2.findEssentialMat(p1, p2, f, pp, cv2.RANSAC, 0.999, 1.0)
+    _, R, T, mask = cv2.recoverPose(E, p1, p2, focal=f, pp=pp, mask=mask)
+    keep = mask.ravel() > 0
+    assert keep.sum() > 300
+    import sfm_opencv_b200 as sfm
+    xyz = sfm.reconstruct(ctx, K, np.eye(3), np.zeros(3), R, T, p1[keep], p2[keep])
+    ref, _ = G.reconstruct(K, np.eye(3), np.zeros(3), R, T, p1[keep], p2[keep])
+    assert G.point_rel_err(xyz, ref).max() < REL_TOL
+
+
+def _resid_close(r, ref):
+    # 1e-5 relative; residuals are differences of ~1e3 px quantities, so floor the scale at 1e-3 px
+    return np.abs(r - ref).max() <= REL_TOL * max(np.abs(ref).max(), 1e-3) and \
+        (np.abs(r - ref) <= REL_TOL * np.maximum(np.abs(ref), 1e-3)).all()
+
+
+@pytest.mark.parametrize("V", [2, 5])
+def test_residuals_vs_oracle(ctx, V):
+    n = 30000
+    sc = synth.scene(n, V, seed=20 + V)
+    cam, pt = synth.observations_camera_major(n, V)
+    obs = sc["xy"].reshape(-1, 2)
+    r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs, huber_delta=4.0)
+    ref = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    assert _resid_close(r, ref)
+    assert abs(cost - G.huber_cost(ref, 4.0)) <= 1e-9 * G.huber_cost(ref, 4.0)
+    _, cost0 = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs, huber_delta=0.0,
+                                       want_resid=False)
+    assert abs(cost0 - G.huber_cost(ref, 0.0)) <= 1e-9 * G.huber_cost(ref, 0.0)
+
+
+def test_residuals_random_order_and_small_angle(ctx):
+    rng = np.random.default_rng(4)
+    n, V = 5000, 4
+    sc = synth.scene(n, V, seed=31)
+    sc["ext"][2, :3] = [1e-9, -2e-9, 3e-9]          # ceres small-angle branch
+    k = 12345
+    cam = rng.integers(0, V, k).astype(np.int32)
+    pt = rng.integers(0, n, k).astype(np.int32)
+    obs = rng.uniform(0, 3000, (k, 2)).astype(np.float32)   # large residuals -> Huber tail
+    r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    ref = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    assert _resid_close(r, ref)
+    assert abs(cost - G.huber_cost(ref, 4.0)) <= 1e-9 * G.huber_cost(ref, 4.0)
+
+
+def test_residual_errors(ctx):
+    import sfm_opencv_b200 as sfm
+    sc = synth.scene(10, 2, seed=1)
+    with pytest.raises(sfm.SfmError):
+        ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], [0, 2], [0, 1], np.zeros((2, 2)))
+    with pytest.raises(sfm.SfmError):
+        ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], [0, 1], [0, 10], np.zeros((2, 2)))
+    r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], [], [], np.zeros((0, 2)))
+    assert r.shape == (0, 2) and cost == 0.0

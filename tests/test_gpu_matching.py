@@ -1,0 +1,195 @@
+"""GPU parity (through the C ABI): sfm_match_pairs vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import matching as M
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _check_pair(ctx_out, q, t):
+    """ctx_out = (matches, min_dist, knn) of one pair; compares with the integer oracle."""
+    m, md, knn = ctx_out
+    d, idx = M.knn2_int(q, t)
+    assert np.array_equal(knn["trainIdx0"], idx[:, 0]), "nearest index differs"
+    assert np.array_equal(knn["trainIdx1"], idx[:, 1]), "second index differs"
+    assert np.array_equal(_bits(knn["distance0"]), _bits(d[:, 0]))
+    assert np.array_equal(_bits(knn["distance1"]), _bits(d[:, 1]))
+    om, od, omd = M.filter_matches(d, idx)
+    assert _bits(md) == _bits(omd)
+    assert np.array_equal(m["queryIdx"], om[:, 0]) and np.array_equal(m["trainIdx"], om[:, 1])
+    assert np.array_equal(_bits(m["distance"]), _bits(od))
+    assert (m["imgIdx"] == 0).all()
+
+
+def _run(ctx, bank, pairs):
+    ctx.upload_descriptors(bank)
+    m, md, knn = ctx.match_pairs(pairs, want_knn=True)
+    for p, (a, b) in enumerate(pairs):
+        _check_pair((m[p], md[p], knn[p]), bank[a], bank[b])
+    return m
+
+
+def test_small_pair(ctx):
+    bank = synth.image_bank(2, 300, seed0=1)
+    _run(ctx, bank, [(0, 1)])
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 2), (1, 257), (127, 255), (128, 256), (129, 257),
+                                   (300, 2), (5, 1000), (1000, 5), (511, 513), (2048, 4100)])
+def test_ragged_sizes(ctx, nq, nt):
+    q = synth.sift_like(nq, 100 + nq)
+    t = synth.sift_like(nt, 200 + nt)
+    k = min(nq, nt) // 3
+    t[:k] = q[:k]                         # exact duplicates: distance 0 rows
+    _run(ctx, [q, t], [(0, 1)])
+
+
+def test_ties_and_duplicates(ctx):
+    t = synth.sift_like(700, 11)
+    t[10] = t[0]; t[20] = t[0]; t[300] = t[299]; t[600] = t[299]; t[699] = t[1]
+    q = np.concatenate([t[:2], t[299:300], synth.sift_like(50, 12)])
+    m = _run(ctx, [q, t], [(0, 1)])
+    ctx.upload_descriptors([q, t])
+    _, _, knn = ctx.match_pairs([(0, 1)], want_knn=True)
+    assert list(knn[0]["trainIdx0"][:3]) == [0, 1, 299]
+    assert list(knn[0]["trainIdx1"][:3]) == [10, 699, 300]
+
+
+def test_tie_across_tiles(ctx):
+    # equal best distances in different 256-row train tiles and chunk boundaries
+    t = synth.sift_like(1200, 21)
+    q = synth.sift_like(40, 22)
+    for r, cols in enumerate([(5, 261), (31, 32), (255, 256), (511, 1023), (1199, 0)]):
+        t[cols[0]] = q[r]; t[cols[1]] = q[r]
+    _run(ctx, [q, t], [(0, 1)])
+
+
+def test_max_values(ctx):
+    # rows at the extremes of the accepted range: 255-valued entries, zero rows
+    q = np.zeros((130, 128), np.uint8); t = np.zeros((300, 128), np.uint8)
+    rng = np.random.default_rng(5)
+    q[:, :30] = rng.integers(200, 256, (130, 30)); t[:, :30] = rng.integers(200, 256, (300, 30))
+    t[7] = 0; q[3] = 0
+    _run(ctx, [q, t], [(0, 1)])
+
+
+def test_float_and_u8_upload_agree(ctx):
+    bank = synth.image_bank(3, 400, seed0=30)
+    ctx.upload_descriptors(bank)
+    a, _, _ = ctx.match_pairs([(0, 1), (1, 2), (0, 2)])
+    ctx.upload_descriptors([b.astype(np.float32) for b in bank])
+    b, _, _ = ctx.match_pairs([(0, 1), (1, 2), (0, 2)])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_consecutive_and_all_pairs_bank(ctx):
+    sizes = [700, 300, 1100, 64, 513]
+    bank = [synth.sift_like(n, 40 + i) for i, n in enumerate(sizes)]
+    for j in range(1, len(bank)):
+        k = min(len(bank[j]), len(bank[j - 1])) // 4
+        bank[j][:k] = bank[j - 1][k:2 * k]
+    _run(ctx, bank, M.consecutive_pairs(len(bank)))
+    _run(ctx, bank, M.all_pairs(len(bank)) + [(3, 0), (2, 2)])
+
+
+def test_reference_shaped_api(ctx):
+    import sfm_opencv_b200 as sfm
+    bank = synth.image_bank(3, 500, seed0=50)
+    ms = sfm.match_features_for_all(ctx, [b.astype(np.float32) for b in bank])
+    assert len(ms) == 2
+    for i, m in enumerate(ms):
+        om, od, _, _, _ = M.match_features(bank[i], bank[i + 1])
+        assert np.array_equal(m["queryIdx"], om[:, 0]) and np.array_equal(m["trainIdx"], om[:, 1])
+    one = sfm.match_features(ctx, bank[0], bank[1])
+    assert np.array_equal(one, ms[0])
+
+
+@pytest.mark.parametrize("name", ["crazyhorse", "desktop"])
+def test_golden_datasets(ctx, golden, name):
+    """Bundled datasets: fixtures hold cv2.BFMatcher-equivalent output (make_golden.py)."""
+    g = golden(name)
+    n = int(g["n_img"])
+    bank = [g[f"desc_{i}"] for i in range(n)]
+    ctx.upload_descriptors(bank)
+    m, md, knn = ctx.match_pairs(M.consecutive_pairs(n), want_knn=True)
+    for i in range(n - 1):
+        assert np.array_equal(knn[i]["trainIdx0"], g[f"knn_idx_{i}"][:, 0])
+        assert np.array_equal(knn[i]["trainIdx1"], g[f"knn_idx_{i}"][:, 1])
+        assert np.array_equal(_bits(knn[i]["distance0"]), _bits(g[f"knn_dist_{i}"][:, 0]))
+        assert np.array_equal(_bits(knn[i]["distance1"]), _bits(g[f"knn_dist_{i}"][:, 1]))
+        assert np.array_equal(m[i]["queryIdx"], g[f"match_{i}"][:, 0])
+        assert np.array_equal(m[i]["trainIdx"], g[f"match_{i}"][:, 1])
+        assert np.array_equal(_bits(m[i]["distance"]), _bits(g[f"match_dist_{i}"]))
+        assert _bits(md[i]) == _bits(g[f"min_dist_{i}"])
+
+
+def test_large_pair_properties(ctx):
+    """8192 x 8192 (BASELINE config 3 pair size): oracle on a row subset + size-independent
+    properties: self-match (q == t -> distance 0 at own index), ascending queryIdx."""
+    bank = synth.image_bank(2, 8192, seed0=60)
+    ctx.upload_descriptors(bank)
+    m, md, knn = ctx.match_pairs([(0, 1), (0, 0)], want_knn=True)
+    rows = np.random.default_rng(0).choice(8192, 512, replace=False)
+    d, idx = M.knn2_int(bank[0][rows], bank[1])
+    assert np.array_equal(knn[0]["trainIdx0"][rows], idx[:, 0])
+    assert np.array_equal(knn[0]["trainIdx1"][rows], idx[:, 1])
+    assert np.array_equal(_bits(knn[0]["distance0"][rows]), _bits(d[:, 0]))
+    assert np.array_equal(_bits(knn[0]["distance1"][rows]), _bits(d[:, 1]))
+    assert (knn[1]["distance0"] == 0).all()
+    # a row's own index is its nearest neighbour unless an identical earlier row exists
+    assert (knn[1]["trainIdx0"] <= np.arange(8192)).all()
+    assert (np.diff(m[0]["queryIdx"]) > 0).all()
+    assert len(m[0]) > 100          # the 20 % shared rows pass the ratio test
+
+
+def test_errors(ctx):
+    import sfm_opencv_b200 as sfm
+    q = synth.sift_like(10, 1)
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.upload_descriptors([q, synth.sift_like(1, 2)])
+        ctx.match_pairs([(0, 1)])
+    assert e.value.code == -7                       # SFM_E_TOO_FEW_TRAIN
+    bad = q.astype(np.float32); bad[3, 5] += 0.5
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.upload_descriptors([bad, q.astype(np.float32)])
+    assert e.value.code == -5                       # SFM_E_NOT_INTEGRAL
+    bad = q.astype(np.float32); bad[0, 0] = 256
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.upload_descriptors([bad, q.astype(np.float32)])
+    assert e.value.code == -6                       # SFM_E_RANGE
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.upload_descriptors([np.zeros((4, 64), np.uint8), np.zeros((4, 64), np.uint8)])
+    assert e.value.code == -4                       # SFM_E_DIM
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.match_pairs([(0, 1)])                   # failed upload left no bank
+    assert e.value.code == -9
+    ctx.upload_descriptors([q, synth.sift_like(20, 3)])
+    with pytest.raises(sfm.SfmError):
+        ctx.match_pairs([(0, 2)])
+    empty, _, _ = ctx.match_pairs([])
+    assert empty == []
+
+
+def test_capacity_error_reports_need(ctx):
+    import ctypes as C
+    import sfm_opencv_b200 as sfm
+    bank = synth.image_bank(2, 600, seed0=70)
+    ctx.upload_descriptors(bank)
+    full, _, _ = ctx.match_pairs([(0, 1)])
+    need = len(full[0])
+    assert need > 2
+    lib = sfm.load()
+    pq = np.array([0], np.int32); pt = np.array([1], np.int32)
+    off = np.zeros(2, np.int64)
+    out = np.zeros(1, sfm.MATCH_DTYPE)
+    rc = lib.sfm_match_pairs(ctx._h, pq.ctypes.data_as(C.POINTER(C.c_int32)),
+                             pt.ctypes.data_as(C.POINTER(C.c_int32)), 1, 0.6, 10.0, 5.0,
+                             out.ctypes.data, 1, off.ctypes.data_as(C.POINTER(C.c_int64)), None, None)
+    assert rc == -8 and off[1] == need

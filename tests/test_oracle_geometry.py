@@ -1,0 +1,56 @@
+"""CPU: triangulation / residual restatements against cv2 and the bundled structure.yml."""
+import numpy as np
+
+from oracle import geometry as G
+from oracle import synth
+
+
+def test_svd_restatement_matches_cv2_triangulate():
+    sc = synth.scene(5000, 2, seed=7)
+    cv = G.triangulate_cv(sc["P"][0], sc["P"][1], sc["xy"][0], sc["xy"][1])
+    sv = G.triangulate_svd(sc["P"], sc["xy"])
+    assert cv.dtype == np.float32 and cv.shape == (4, 5000)
+    assert np.allclose(np.linalg.norm(cv, axis=0), 1.0, atol=1e-6)
+    err = G.point_rel_err(G.dehomogenize(sv), G.dehomogenize(cv))
+    assert err.max() < 1e-5          # tolerance of north_star for triangulated points
+
+
+def test_triangulation_recovers_noiseless_points():
+    sc = synth.scene(2000, 4, seed=3, noise_px=0.0)
+    xyz = G.dehomogenize(G.triangulate_svd(sc["P"], sc["xy"]))
+    assert G.point_rel_err(xyz, sc["X"]).max() < 1e-3   # float32 observations / projections
+
+
+def test_residuals_match_cv2_project_points():
+    import cv2
+    sc = synth.scene(3000, 3, seed=9)
+    cam, pt = synth.observations_camera_major(3000, 3)
+    obs = sc["xy"].reshape(-1, 2)
+    r = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    K = np.array([[sc["intr"][0], 0, sc["intr"][2]], [0, sc["intr"][1], sc["intr"][3]], [0, 0, 1]])
+    for v in range(3):
+        proj, _ = cv2.projectPoints(sc["X"], sc["ext"][v, :3], sc["ext"][v, 3:], K, None)
+        ref = proj.reshape(-1, 2) - obs[v * 3000:(v + 1) * 3000].astype(np.float64)
+        assert np.abs(ref - r[v * 3000:(v + 1) * 3000]).max() < 1e-9
+    assert 0.2 < np.sqrt((r ** 2).mean()) < 1.0          # ~0.5 px noise
+
+
+def test_small_angle_branch():
+    w = np.array([[1e-9, -2e-9, 3e-9]])
+    X = np.array([[1.0, 2.0, 3.0]])
+    assert np.allclose(G.angle_axis_rotate(w, X), X + np.cross(w, X), rtol=0, atol=1e-18)
+
+
+def test_huber_cost():
+    r = np.array([[3.0, 0.0], [0.0, 5.0]])
+    # s = 9 (<=16 -> 9), s = 25 (-> 8*5-16 = 24); cost = 0.5*33
+    assert G.huber_cost(r, 4.0) == 16.5
+    assert G.huber_cost(r, 0.0) == 17.0
+
+
+def test_observation_order_is_camera_major():
+    ids = [[0, -1, 2], [-1, 1, 0]]
+    kps = [np.arange(6, dtype=np.float32).reshape(3, 2), 10 + np.arange(6, dtype=np.float32).reshape(3, 2)]
+    cam, pt, obs = G.enumerate_observations(ids, kps)
+    assert list(cam) == [0, 0, 1, 1] and list(pt) == [0, 2, 1, 0]
+    assert obs.tolist() == [[0, 1], [4, 5], [12, 13], [14, 15]]
