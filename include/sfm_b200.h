@@ -123,6 +123,12 @@ SFM_API int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* 
                     sfm_match_t* out, int64_t out_cap, int64_t* offsets,
                     sfm_knn2_t* knn_raw, float* min_dist);
 
+/* Copies the kept matches of the most recent sfm_match_pairs call (they stay resident on
+ * the device) to `out`.  Lets a caller size the buffer exactly: call sfm_match_pairs with
+ * out = NULL / out_cap = 0 (returns SFM_E_CAPACITY when there are matches, offsets filled),
+ * allocate offsets[n_pairs] entries, then fetch -- the kNN is not recomputed. */
+SFM_API int sfm_fetch_matches(sfm_ctx* ctx, sfm_match_t* out, int64_t out_cap);
+
 /* Device-resident variant used to time the kernels without PCIe: runs the same
  * kernels, keeps results on the device, returns only the total number of kept
  * matches. kernel_ms (nullable) receives the CUDA-event time of the kNN kernel alone,
@@ -182,6 +188,13 @@ SFM_API int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops);
 
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 SFM_API int64_t sfm_launch_count(const sfm_ctx* ctx);
+
+/* CUDA-event stopwatch on the context's own stream (torch.cuda.Event only sees torch's
+ * stream): sfm_timer_start records, sfm_timer_stop records + synchronises and returns the
+ * device time in ms of everything the context enqueued in between. */
+SFM_API int sfm_timer_start(sfm_ctx* ctx);
+SFM_API int sfm_timer_stop(sfm_ctx* ctx, float* ms);
+SFM_API int sfm_sync(sfm_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ SYMBOLS = {
     "sfm_upload_descriptors": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_upload_descriptors_u8": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_match_pairs": (_i, [_vp, _pi, _pi, _i, _d, _f, _f, _vp, _i64, _pi64, _vp, _pf]),
+    "sfm_fetch_matches": (_i, [_vp, _vp, _i64]),
     "sfm_match_pairs_resident": (_i, [_vp, _pi, _pi, _i, _d, _f, _f, _pi64, _pf, _pf]),
     "sfm_triangulate_batch": (_i, [_vp, _pf, _pf, _i, _i64, _pf, _pd]),
     "sfm_reproject_residuals": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _d, _pd, _pd]),
@@ -41,6 +42,9 @@ SYMBOLS = {
     "sfm_reproject_residuals_timed": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _d, _pd, _pd, _i, _pf]),
     "sfm_probe_i8_peak": (_i, [_vp, _i, _pd]),
     "sfm_launch_count": (_i64, [_vp]),
+    "sfm_timer_start": (_i, [_vp]),
+    "sfm_timer_stop": (_i, [_vp, _pf]),
+    "sfm_sync": (_i, [_vp]),
 }
 
 _lib = None

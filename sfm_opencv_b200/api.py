@@ -41,11 +41,23 @@ class Context:
             raise SfmError(err.value, self._lib.sfm_last_error(None).decode())
         self.device = device
         self.n_desc: list[int] = []
+        self._arenas: dict[str, tuple[int, int]] = {}
+        self.last_d2h_bytes = 0
 
     def close(self):
         if getattr(self, "_h", None):
+            for p, _ in self._arenas.values():
+                self._lib.sfm_host_free(p)
+            self._arenas = {}
             self._lib.sfm_destroy(self._h)
             self._h = None
+
+    def pinned_empty(self, shape, dtype, name: str) -> np.ndarray:
+        """A numpy array backed by pinned host memory owned by this context (for callers
+        that want asynchronous, full-rate H2D copies of their descriptor banks)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        return self._pinned(name, max(n, 1))[:n].view(dt).reshape(shape)
 
     def __enter__(self):
         return self
@@ -84,25 +96,55 @@ class Context:
         self._check(fn(self._h, len(descs), ptrs, _ptr(n, C.c_int32), dim))
         self.n_desc = [int(x) for x in n]
 
+    def _pinned(self, name: str, nbytes: int) -> np.ndarray:
+        """Grow-only pinned host arena (cudaMallocHost through the C ABI) viewed as uint8."""
+        cur = self._arenas.get(name)
+        if cur is None or cur[1] < nbytes:
+            if cur is not None:
+                self._lib.sfm_host_free(cur[0])
+            cap = max(int(nbytes * 1.25), 1 << 16)
+            p = self._lib.sfm_host_alloc(cap)
+            if not p:
+                raise SfmError(_capi.SFM_E_NOMEM, "pinned host allocation failed")
+            cur = (p, cap)
+            self._arenas[name] = cur
+        buf = (C.c_uint8 * cur[1]).from_address(cur[0])
+        return np.frombuffer(buf, np.uint8, nbytes)
+
     def match_pairs(self, pairs, ratio=RATIO, dist_floor=DIST_FLOOR, gate_mult=GATE_MULT,
-                    want_knn=False):
+                    want_knn=False, copy=True):
         """pairs: iterable of (query_img, train_img). Returns (list of match arrays per pair,
-        min_dist[n_pairs], knn list or None)."""
+        min_dist[n_pairs], knn list or None).
+
+        Two C-ABI calls: sfm_match_pairs sizes the result (offsets), sfm_fetch_matches copies
+        exactly offsets[n_pairs] matches into a pinned buffer.  With copy=False the returned
+        arrays are views of that buffer and are overwritten by the next call."""
         pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
         n_pairs = pairs.shape[0]
         pq = np.ascontiguousarray(pairs[:, 0])
         pt = np.ascontiguousarray(pairs[:, 1])
         if ((pq < 0) | (pq >= len(self.n_desc)) | (pt < 0) | (pt >= len(self.n_desc))).any():
             raise SfmError(_capi.SFM_E_INVALID, "pair index out of range")
-        rows = int(sum(self.n_desc[q] for q in pq))
         offsets = np.zeros(n_pairs + 1, np.int64)
         min_dist = np.zeros(max(n_pairs, 1), np.float32)
-        out = np.zeros(max(rows, 1), MATCH_DTYPE)         # at most one match per query row
-        knn = np.zeros(max(rows, 1), KNN_DTYPE) if want_knn else None
-        self._check(self._lib.sfm_match_pairs(
+        knn = None
+        if want_knn:
+            rows = int(sum(self.n_desc[q] for q in pq))
+            knn = np.zeros(max(rows, 1), KNN_DTYPE)
+        rc = self._lib.sfm_match_pairs(
             self._h, _ptr(pq, C.c_int32), _ptr(pt, C.c_int32), n_pairs, ratio, dist_floor,
-            gate_mult, out.ctypes.data, rows, _ptr(offsets, C.c_int64),
-            knn.ctypes.data if want_knn else None, _ptr(min_dist, C.c_float)))
+            gate_mult, None, 0, _ptr(offsets, C.c_int64),
+            knn.ctypes.data if want_knn else None, _ptr(min_dist, C.c_float))
+        if rc not in (0, _capi.SFM_E_CAPACITY):
+            self._check(rc)
+        total = int(offsets[n_pairs])
+        raw = self._pinned("matches", max(total, 1) * MATCH_DTYPE.itemsize)
+        out = raw.view(MATCH_DTYPE)[:max(total, 1)]
+        if total:
+            self._check(self._lib.sfm_fetch_matches(self._h, out.ctypes.data, total))
+        if copy:
+            out = out.copy()
+        self.last_d2h_bytes = total * MATCH_DTYPE.itemsize + offsets.nbytes + 4 * n_pairs
         matches = [out[offsets[p]:offsets[p + 1]] for p in range(n_pairs)]
         knn_list = None
         if want_knn:
@@ -171,6 +213,19 @@ class Context:
             return resid, (cost.value if want_cost else None), ms.value
         self._check(self._lib.sfm_reproject_residuals(*args))
         return resid, (cost.value if want_cost else None)
+
+    # ------------------------------------------------------------------ timing hooks
+    def timer_start(self):
+        self._check(self._lib.sfm_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Device time in ms (CUDA events on the context's stream) since timer_start()."""
+        ms = C.c_float(0)
+        self._check(self._lib.sfm_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self._lib.sfm_sync(self._h))
 
     def probe_i8_peak(self, iters: int = 2000) -> float:
         tops = C.c_double(0)

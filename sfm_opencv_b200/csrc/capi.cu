@@ -79,6 +79,7 @@ struct sfm_ctx {
   int n_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tev[2] = {nullptr, nullptr};   // sfm_timer_start / sfm_timer_stop
   std::string err;
   int64_t launches = 0;
   EncodeTiledFn encode = nullptr;
@@ -92,6 +93,12 @@ struct sfm_ctx {
 
   // matching scratch
   DevBuf pairs, items, knn, counts, offsets, min_dist, out, knn_f;
+  // result of the last sfm_match_pairs call, kept resident for sfm_fetch_matches
+  bool last_valid = false, last_written = false;
+  int64_t last_total = 0;
+  int last_n_pairs = 0;
+  double last_ratio = 0.0;
+  float last_floor = 0.f, last_mult = 0.f;
   // geometry scratch
   DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
 };
@@ -163,6 +170,7 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     return bail(SFM_E_CUDA, "cudaStreamCreate failed");
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  for (auto& ev : ctx->tev) cudaEventCreate(&ev);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
@@ -188,6 +196,8 @@ void sfm_destroy(sfm_ctx* ctx) {
   for (DevBuf* b : bufs) b->release();
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->tev)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -202,6 +212,29 @@ void sfm_host_free(void* p) {
 }
 
 int64_t sfm_launch_count(const sfm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sfm_sync(sfm_ctx* ctx) {
+  if (!ctx) return SFM_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
+}
+
+int sfm_timer_start(sfm_ctx* ctx) {
+  if (!ctx) return SFM_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return SFM_OK;
+}
+
+int sfm_timer_stop(sfm_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return SFM_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->tev[1]));
+  CK(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
+  return SFM_OK;
+}
 
 // ----------------------------------------------------------------------------- upload
 static int make_tmap(sfm_ctx* ctx, CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows) {
@@ -228,6 +261,7 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   if (dim != kDim) return fail(ctx, SFM_E_DIM, "descriptor dimension must be 128 (SIFT)");
   CK(cudaSetDevice(ctx->device));
   ctx->bank_ready = false;
+  ctx->last_valid = false;
   ctx->img_n.assign(n_desc, n_desc + n_img);
   ctx->img_row0.resize(n_img);
   int64_t rows = 0;
@@ -347,6 +381,30 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   return SFM_OK;
 }
 
+// Writes the kept matches of the last sfm_match_pairs* call (still resident) to the host.
+static int fetch_matches(sfm_ctx* ctx, sfm_match_t* out, int64_t out_cap) {
+  const int64_t total = ctx->last_total;
+  if (total > out_cap) {
+    ctx->err = "output capacity too small; offsets[n_pairs] holds the required size";
+    return SFM_E_CAPACITY;
+  }
+  if (total > 0) {
+    if (!ctx->last_written) {
+      CK(ctx->out.ensure(sizeof(sfm_match_t) * total));
+      CK(launch_filter_write(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), ctx->last_n_pairs,
+                             ctx->last_ratio, ctx->last_floor, ctx->last_mult,
+                             ctx->min_dist.as<float>(), ctx->offsets.as<int64_t>(),
+                             ctx->out.as<sfm_match_t>(), total, ctx->stream));
+      ctx->launches += 1;
+      ctx->last_written = true;
+    }
+    CK(cudaMemcpyAsync(out, ctx->out.p, sizeof(sfm_match_t) * total, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFM_OK;
+}
+
 int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, int n_pairs,
                     double ratio, float dist_floor, float gate_mult, sfm_match_t* out,
                     int64_t out_cap, int64_t* offsets, sfm_knn2_t* knn_raw, float* min_dist) {
@@ -354,6 +412,7 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
   if (!offsets) return fail(ctx, SFM_E_INVALID, "offsets must not be null");
   if (out_cap < 0 || (out_cap > 0 && !out)) return fail(ctx, SFM_E_INVALID, "bad output buffer");
   int64_t rows = 0;
+  ctx->last_valid = false;
   int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, false);
   if (rc) return rc;
   CK(cudaMemcpyAsync(offsets, ctx->offsets.p, 8 * (n_pairs + 1), cudaMemcpyDeviceToHost,
@@ -369,23 +428,22 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
                        ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  const int64_t total = offsets[n_pairs];
-  if (total > out_cap) {
-    ctx->err = "output capacity too small; offsets[n_pairs] holds the required size";
-    return SFM_E_CAPACITY;
-  }
-  if (total > 0) {
-    CK(ctx->out.ensure(sizeof(sfm_match_t) * total));
-    CK(launch_filter_write(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio,
-                           dist_floor, gate_mult, ctx->min_dist.as<float>(),
-                           ctx->offsets.as<int64_t>(), ctx->out.as<sfm_match_t>(), total,
-                           ctx->stream));
-    ctx->launches += 1;
-    CK(cudaMemcpyAsync(out, ctx->out.p, sizeof(sfm_match_t) * total, cudaMemcpyDeviceToHost,
-                       ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
-  return SFM_OK;
+  ctx->last_total = offsets[n_pairs];
+  ctx->last_n_pairs = n_pairs;
+  ctx->last_ratio = ratio;
+  ctx->last_floor = dist_floor;
+  ctx->last_mult = gate_mult;
+  ctx->last_written = false;
+  ctx->last_valid = true;
+  return fetch_matches(ctx, out, out_cap);
+}
+
+int sfm_fetch_matches(sfm_ctx* ctx, sfm_match_t* out, int64_t out_cap) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!ctx->last_valid) return fail(ctx, SFM_E_INVALID, "no sfm_match_pairs result to fetch");
+  if (out_cap < 0 || (out_cap > 0 && !out)) return fail(ctx, SFM_E_INVALID, "bad output buffer");
+  CK(cudaSetDevice(ctx->device));
+  return fetch_matches(ctx, out, out_cap);
 }
 
 int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
@@ -393,6 +451,7 @@ int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t*
                              int64_t* total_matches, float* kernel_ms, float* total_ms) {
   if (!ctx) return SFM_E_INVALID;
   int64_t rows = 0;
+  ctx->last_valid = false;
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
   int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, true);
