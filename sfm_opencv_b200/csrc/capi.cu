@@ -14,8 +14,8 @@
 
 namespace sfm {
 // match_knn.cu
-cudaError_t launch_knn2(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const int32_t* ckey,
-                        const int32_t* norm, const PairDesc* pairs, const WorkItem* items,
+cudaError_t launch_knn2(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* norm,
+                        const PairDesc* pairs, const int32_t* item_prefix, int n_pairs,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 // match_finalize.cu
@@ -89,7 +89,7 @@ struct sfm_ctx {
   std::vector<int32_t> img_n, img_row0;
   int64_t bank_rows = 0;
   bool bank_ready = false;
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap;   // u8 bank, box = 128 rows x 128 bytes, 128-byte swizzle
 
   // matching scratch
   DevBuf pairs, items, knn, counts, offsets, min_dist, out, knn_f;
@@ -303,9 +303,7 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   if (flags & 4u)
     return fail(ctx, SFM_E_RANGE,
                 "descriptor row norm^2 >= 2^21: float sqrt no longer injective on the distances");
-  int rc = make_tmap(ctx, &ctx->tmap_a, ctx->desc.p, static_cast<uint64_t>(rows), kTileM);
-  if (rc) return rc;
-  rc = make_tmap(ctx, &ctx->tmap_b, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
+  int rc = make_tmap(ctx, &ctx->tmap, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
   if (rc) return rc;
   ctx->bank_ready = true;
   return SFM_OK;
@@ -335,8 +333,8 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   CK(cudaSetDevice(ctx->device));
   const int n_img = static_cast<int>(ctx->img_n.size());
   std::vector<PairDesc> pairs(n_pairs);
-  std::vector<WorkItem> items;
-  int64_t rows = 0;
+  std::vector<int32_t> prefix(n_pairs + 1);   // work items (256-row query blocks) before pair p
+  int64_t rows = 0, n_items = 0;
   for (int p = 0; p < n_pairs; ++p) {
     const int q = pair_q[p], t = pair_t[p];
     if (q < 0 || q >= n_img || t < 0 || t >= n_img)
@@ -351,13 +349,14 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     pd.nt = ctx->img_n[t];
     pd.knn_off = rows;
     rows += pd.nq;
-    const int mt = (pd.nq + kTileM - 1) / kTileM;
-    for (int m = 0; m < mt; ++m) items.push_back(WorkItem{p, m});
+    prefix[p] = static_cast<int32_t>(n_items);
+    n_items += (pd.nq + kTileM - 1) / kTileM;
+    if (n_items > INT32_MAX) return fail(ctx, SFM_E_INVALID, "too many query blocks");
   }
+  prefix[n_pairs] = static_cast<int32_t>(n_items);
   *total_rows = rows;
-  if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many tiles");
   CK(ctx->pairs.ensure(sizeof(PairDesc) * (n_pairs + 1)));
-  CK(ctx->items.ensure(sizeof(WorkItem) * (items.size() + 1)));
+  CK(ctx->items.ensure(sizeof(int32_t) * (n_pairs + 1)));
   CK(ctx->knn.ensure(sizeof(Knn2) * (rows + 1)));
   CK(ctx->counts.ensure(4 * (n_pairs + 1)));
   CK(ctx->offsets.ensure(8 * (n_pairs + 1)));
@@ -365,14 +364,13 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   if (n_pairs)
     CK(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), sizeof(PairDesc) * n_pairs,
                        cudaMemcpyHostToDevice, ctx->stream));
-  if (!items.empty())
-    CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(WorkItem) * items.size(),
-                       cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->items.p, prefix.data(), sizeof(int32_t) * (n_pairs + 1),
+                     cudaMemcpyHostToDevice, ctx->stream));
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(launch_knn2(ctx->tmap_a, ctx->tmap_b, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
-                 ctx->pairs.as<PairDesc>(), ctx->items.as<WorkItem>(),
-                 static_cast<int>(items.size()), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
-  if (!items.empty()) ctx->launches += 1;
+  CK(launch_knn2(ctx->tmap, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
+                 ctx->pairs.as<PairDesc>(), ctx->items.as<int32_t>(), n_pairs,
+                 static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+  if (n_items > 0) ctx->launches += 1;
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
                    gate_mult, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
@@ -636,7 +634,7 @@ int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops) {
   ctx->launches += 2;
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  const double ops = 2.0 * kTileM * kTileN * 32.0 * 4.0 * iters * ctx->n_sms;
+  const double ops = 2.0 * 128.0 * 256.0 * 32.0 * 4.0 * iters * ctx->n_sms;   // probe tile 128x256
   *tops = ops / (ms * 1e-3) / 1e12;
   return SFM_OK;
 }

@@ -5,8 +5,9 @@
 namespace sfm {
 
 constexpr int kDim = 128;          // SIFT descriptor length in bytes (u8)
-constexpr int kTileM = 128;        // query rows per work item (TMEM lanes)
-constexpr int kTileN = 256;        // train rows per MMA tile (TMEM columns)
+constexpr int kTileM = 256;        // query rows per work item (two 128-lane TMEM halves)
+constexpr int kTileN = 128;        // train rows per B tile (TMEM columns per half)
+constexpr int kKeyShift = 7;       // packed key = (|t|^2 - 2 q.t) << 7 | (train row & 127)
 constexpr int kRowPad = 256;       // every image is padded to a multiple of this many rows
 constexpr int kNormPad = 0x7FFFFF; // norm^2 sentinel of padding rows (never selected)
 
@@ -17,12 +18,6 @@ struct PairDesc {
   int32_t nq;        // query descriptors
   int32_t nt;        // train descriptors
   int64_t knn_off;   // first row of this pair in the kNN result array
-};
-
-// One work item = one 128-row query tile of one pair, swept over all train tiles.
-struct WorkItem {
-  int32_t pair;
-  int32_t mtile;
 };
 
 // Raw kNN result per query row: exact integer squared distances.

@@ -46,17 +46,15 @@ __global__ void __launch_bounds__(512, 1) ldtm_kernel(int iters, int wait_every,
   }
 }
 
-// kind: 7 fused add+min (VIADDMNMX); 0 imad, 1 min2, 2 min3, 3 shift-add (lea), 4 imad+min3 (1:0.5), 5 iadd3, 6 fadd-ish fma
+// Integer pipe throughput with volatile PTX (ptxas keeps every op):
+// 0 imad  1 min2  2 min3  3 add+min (VIADDMNMX)  4 xor (LOP3)  5 iadd3  6 ffma
+// 7 imad + 0.5 min3 (top-1 key stream)  8 imad-imm (x*-256+y)  9 setp+selp  10 max2+min3 (merge)
 template <int KIND>
 __global__ void __launch_bounds__(512, 1) alu_kernel(int iters, int a0, int b0, long long* cyc,
                                                     int* sink) {
-  int x[8];
+  int x[8], y[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) x[k] = threadIdx.x * 7 + k * a0;
-  int a = a0 + threadIdx.x, b = b0 - threadIdx.x;
-  int y[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) y[k] = threadIdx.x * 13 + k * b0;
+  for (int k = 0; k < 8; ++k) { x[k] = threadIdx.x * 7 + k * a0; y[k] = threadIdx.x * 13 + k * b0; }
   __syncthreads();
   const long long t0 = clock64();
   for (int i = 0; i < iters; ++i) {
@@ -64,19 +62,26 @@ __global__ void __launch_bounds__(512, 1) alu_kernel(int iters, int a0, int b0, 
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (KIND == 0) x[k] = x[k] * a + b;
-        if (KIND == 1) x[k] = min(x[k] ^ a, b + k);
-        if (KIND == 2) x[k] = __vimin3_s32(x[k], a + k, b ^ x[(k + 1) & 7]);
-        if (KIND == 3) x[k] = (x[k] << 9) + a;
-        if (KIND == 4) {
-          const int key = x[k] * -512 + a;
-          if (k & 1) x[k] = __vimin3_s32(x[k], key, x[k - 1]); else x[k] = key + b;
+        if (KIND == 0) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 1) {
+          if (u & 1) asm volatile("min.s32 %0, %0, %1;" : "+r"(x[k]) : "r"(y[k]));
+          else asm volatile("max.s32 %0, %0, %1;" : "+r"(x[k]) : "r"(y[(k + 3) & 7]));
         }
-        if (KIND == 5) x[k] = x[k] + a + b;
-        if (KIND == 6) x[k] = __float_as_int(__int_as_float(x[k]) * 1.0001f + 0.5f);
-        if (KIND == 7) x[k] = min(x[k], y[k] + a);
+        if (KIND == 2) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 3) asm volatile("{.reg .s32 t; add.s32 t, %1, %2; min.s32 %0, t, %0;}" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 4) asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[k]) : "r"(y[k]));
+        if (KIND == 5) asm volatile("{.reg .s32 t; add.s32 t, %0, %1; add.s32 %0, t, %2;}" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 6) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 7) {
+          int t;
+          asm volatile("mad.lo.s32 %0, %1, -256, %2;" : "=r"(t) : "r"(y[k]), "r"(x[k >> 1]));
+          if (k & 1) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(x[k >> 1]) : "r"(t), "r"(x[4 + (k >> 1)]));
+          else x[4 + (k >> 1)] = t;
+        }
+        if (KIND == 8) asm volatile("mad.lo.s32 %0, %0, -256, %1;" : "+r"(x[k]) : "r"(y[k]));
+        if (KIND == 9) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; selp.s32 %0, %2, %0, p;}" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 10) asm volatile("{.reg .s32 t, u; max.s32 t, %0, %2; min.s32 %0, %0, %2; min.s32 u, t, %1; min.s32 %1, u, %3;}" : "+r"(x[k]), "+r"(y[k]) : "r"(y[(k + 1) & 7]), "r"(y[(k + 2) & 7]));
       }
-      a += 3; b -= 5;
     }
   }
   __syncthreads();
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(512, 1) alu_kernel(int iters, int a0, int b0, 
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
   int s = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s ^= x[k];
+  for (int k = 0; k < 8; ++k) s ^= x[k] ^ y[k];
   if (s == 0x7fffffff) sink[0] = s;
 }
 
@@ -115,26 +120,19 @@ int main() {
              (double)iters * warps * 4096.0 / c);
     }
   }
-  const char* names[] = {"imad", "min2", "min3", "shladd", "imad_min3_mix", "iadd3", "ffma", "viaddmnmx"};
+  const char* names[] = {"imad", "min2", "min3", "addmin", "xor", "iadd3", "ffma", "imad_halfmin3",
+                         "imad_imm", "setp_selp", "merge_top2"};
   for (int warps : {4, 8, 16}) {
-    for (int kind = 0; kind < 8; ++kind) {
+    for (int kind = 0; kind < 11; ++kind) {
       const int it = 2000;
       for (int rep = 0; rep < 2; ++rep) {
-        switch (kind) {
-          case 0: alu_kernel<0><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 1: alu_kernel<1><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 2: alu_kernel<2><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 3: alu_kernel<3><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 4: alu_kernel<4><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 5: alu_kernel<5><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 6: alu_kernel<6><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-          case 7: alu_kernel<7><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-        }
+#define RUN(K) case K: alu_kernel<K><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
+        switch (kind) { RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) }
       }
       if (cudaDeviceSynchronize() != cudaSuccess) { printf(", \"error\": \"alu\"}\n"); return 1; }
       const double c = (double)maxcyc(cyc, n_sms);
-      // source-level ops per thread: it * 4 * 8
-      printf(", \"%s_srcops_per_clk_sm_w%d\": %.1f", names[kind], warps,
+      // asm blocks per thread: it * 4 * 8
+      printf(", \"%s_blocks_per_clk_sm_w%d\": %.1f", names[kind], warps,
              (double)it * 32.0 * warps * 32.0 / c);
     }
   }
