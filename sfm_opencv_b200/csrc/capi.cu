@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -14,8 +15,8 @@
 
 namespace sfm {
 // match_knn.cu
-cudaError_t launch_knn2(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* norm,
-                        const PairDesc* pairs, const int32_t* item_prefix, int n_pairs,
+cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
+                        const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 // match_finalize.cu
@@ -82,11 +83,13 @@ struct sfm_ctx {
   cudaEvent_t tev[2] = {nullptr, nullptr};   // sfm_timer_start / sfm_timer_stop
   std::string err;
   int64_t launches = 0;
+  int knn_mode = 1;   // SFM_KNN_MODE env: 0 = unfiltered epilogue (A/B testing)
   EncodeTiledFn encode = nullptr;
 
   // descriptor bank (padded rows)
   DevBuf desc, norm, ckey, flags, stage;
   std::vector<int32_t> img_n, img_row0;
+  std::vector<int2> h_items;                   // reused host staging of the work-item table
   int64_t bank_rows = 0;
   bool bank_ready = false;
   CUtensorMap tmap;   // u8 bank, box = 128 rows x 128 bytes, 128-byte swizzle
@@ -180,6 +183,7 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     return bail(SFM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (const char* m = getenv("SFM_KNN_MODE")) ctx->knn_mode = atoi(m);
   if (err) *err = SFM_OK;
   return ctx;
 }
@@ -333,8 +337,9 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   CK(cudaSetDevice(ctx->device));
   const int n_img = static_cast<int>(ctx->img_n.size());
   std::vector<PairDesc> pairs(n_pairs);
-  std::vector<int32_t> prefix(n_pairs + 1);   // work items (256-row query blocks) before pair p
-  int64_t rows = 0, n_items = 0;
+  std::vector<int2>& items = ctx->h_items;    // work items: (pair, 256-row query block)
+  items.clear();
+  int64_t rows = 0;
   for (int p = 0; p < n_pairs; ++p) {
     const int q = pair_q[p], t = pair_t[p];
     if (q < 0 || q >= n_img || t < 0 || t >= n_img)
@@ -349,14 +354,14 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     pd.nt = ctx->img_n[t];
     pd.knn_off = rows;
     rows += pd.nq;
-    prefix[p] = static_cast<int32_t>(n_items);
-    n_items += (pd.nq + kTileM - 1) / kTileM;
-    if (n_items > INT32_MAX) return fail(ctx, SFM_E_INVALID, "too many query blocks");
+    const int mb = (pd.nq + kTileM - 1) / kTileM;
+    for (int m = 0; m < mb; ++m) items.push_back(make_int2(p, m));
+    if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many query blocks");
   }
-  prefix[n_pairs] = static_cast<int32_t>(n_items);
+  const int64_t n_items = static_cast<int64_t>(items.size());
   *total_rows = rows;
   CK(ctx->pairs.ensure(sizeof(PairDesc) * (n_pairs + 1)));
-  CK(ctx->items.ensure(sizeof(int32_t) * (n_pairs + 1)));
+  CK(ctx->items.ensure(sizeof(int2) * (n_items + 1)));
   CK(ctx->knn.ensure(sizeof(Knn2) * (rows + 1)));
   CK(ctx->counts.ensure(4 * (n_pairs + 1)));
   CK(ctx->offsets.ensure(8 * (n_pairs + 1)));
@@ -364,12 +369,12 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   if (n_pairs)
     CK(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), sizeof(PairDesc) * n_pairs,
                        cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->items.p, prefix.data(), sizeof(int32_t) * (n_pairs + 1),
-                     cudaMemcpyHostToDevice, ctx->stream));
+  if (n_items)
+    CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(int2) * n_items, cudaMemcpyHostToDevice,
+                       ctx->stream));
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(launch_knn2(ctx->tmap, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
-                 ctx->pairs.as<PairDesc>(), ctx->items.as<int32_t>(), n_pairs,
-                 static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+  CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
+                 ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(), static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
   if (n_items > 0) ctx->launches += 1;
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
@@ -624,7 +629,7 @@ int sfm_reproject_residuals_timed(sfm_ctx* ctx, const double intr[4], const doub
 // ----------------------------------------------------------------------------- probe
 int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops) {
   if (!ctx) return SFM_E_INVALID;
-  if (iters <= 0 || !tops) return fail(ctx, SFM_E_INVALID, "bad probe arguments");
+  if (iters == 0 || !tops) return fail(ctx, SFM_E_INVALID, "bad probe arguments");
   CK(cudaSetDevice(ctx->device));
   CK(launch_i8_peak(iters, ctx->n_sms, ctx->stream));   // warm-up
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -634,7 +639,7 @@ int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops) {
   ctx->launches += 2;
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  const double ops = 2.0 * 128.0 * 256.0 * 32.0 * 4.0 * iters * ctx->n_sms;   // probe tile 128x256
+  const double ops = 2.0 * 128.0 * 256.0 * 32.0 * 4.0 * (iters > 0 ? iters : (-iters) >> 4) * ctx->n_sms;   // probe tile 128x256
   *tops = ops / (ms * 1e-3) / 1e12;
   return SFM_OK;
 }

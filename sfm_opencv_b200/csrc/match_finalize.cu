@@ -53,7 +53,7 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
   if (s > kMaxNorm) bad |= kFlagNorm;
   if (lane == 0) {
     norm[row0 + r] = s;
-    ckey[row0 + r] = (s << kKeyShift) | (r & (kTileN - 1));
+    ckey[row0 + r] = (s << (kKeyShift + 1)) | (r & (2 * kTileN - 1));
   }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (bad && lane == 0) atomicOr(flags, bad);
@@ -65,7 +65,7 @@ __global__ void pad_rows_kernel(int n, int n_pad, int row0, int32_t* __restrict_
   const int r = n + blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_pad) {
     norm[row0 + r] = kNormPad;
-    ckey[row0 + r] = (kNormPad << kKeyShift) | (r & (kTileN - 1));
+    ckey[row0 + r] = (kNormPad << (kKeyShift + 1)) | (r & (2 * kTileN - 1));
   }
 }
 

@@ -8,11 +8,18 @@
 // swept over all 128-row train tiles of the pair:
 //   warp 0       TMA producer : the 256-row A block once per item (2 x 16 KB), B tiles
 //                               (128 train rows, 16 KB) + their column keys through a ring
-//   warp 1       MMA issuer   : per B tile 2 x 4 MMAs (128x128x32): query half h -> TMEM
-//                               accumulator [buf][h]; every B byte feeds 256 query rows
-//   warp 2       TMEM allocator (512 columns = 2 buffers x 2 halves x 128)
-//   warps 4..11  epilogue     : one thread per query row (TMEM lane); tcgen05.ld, packed
-//                               (distance,index) keys, exact running top-2
+//   warps 4..7   MMA issuers  : warp (h, p) issues the 4 MMAs (128x128x32) of query half h for
+//                               the tiles of parity p into TMEM accumulator [p][h]; every B
+//                               byte feeds 256 query rows.  Four issuers because a
+//                               tcgen05.mma / commit / mbarrier wait each stall the issuing
+//                               thread for 50-100 cycles (measured, tools/exp_probe.py): one
+//                               thread cannot keep the tensor pipe busy at 64 cycles per MMA
+//                               (512 TMEM columns = 2 buffers x 2 halves x 128)
+//   warps 8..23  epilogue     : 16 warps = 2 query halves x 2 column halves x 4 TMEM lane
+//                               quarters; a thread owns one query row and 64 of the 128
+//                               columns of every tile: tcgen05.ld, packed (distance,index)
+//                               keys, threshold-filtered exact top-2; the two column halves of
+//                               a row are merged once per item through shared memory
 // The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -27,10 +34,16 @@ namespace sfm {
 constexpr int kStages = 6;                      // B-tile ring depth (16 KB each)
 constexpr int kAccBufs = 2;                     // TMEM accumulator buffers (2 x 128 columns each)
 constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
-constexpr int kFirstEpiWarp = 4;
-constexpr int kEpiWarps = 8;                    // 2 halves x 4 TMEM lane quarters
+constexpr int kFirstMmaWarp = 4;                // warps 1..3 idle (warpgroup granularity)
+constexpr int kMmaWarps = 4;                    // (query half, tile parity)
+constexpr int kFirstEpiWarp = kFirstMmaWarp + kMmaWarps;
+constexpr int kRegsCtl = 48;                    // setmaxnreg: producer / MMA warpgroups
+constexpr int kRegsEpi = 96;                    // setmaxnreg: epilogue warpgroups
+static_assert(8 * kRegsCtl + 16 * kRegsEpi <= 24 * 80, "register pool of the CTA (768 x 80)");
+constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
 constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
+constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
 
 constexpr uint32_t kABytes = kTileM * kDim;     // 32 KB
 constexpr uint32_t kAHalfBytes = kHalfM * kDim; // 16 KB
@@ -51,7 +64,8 @@ constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + 2 * kABytes;
 constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
 constexpr uint32_t kOffInfo = kOffCk + kCkSlots * kCkBytes;
-constexpr uint32_t kOffBar = kOffInfo + 2 * sizeof(ItemInfo);
+constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
+constexpr uint32_t kOffBar = kOffMerge + 2 * kTileM * 16;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kKnnSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
@@ -63,37 +77,89 @@ __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
   a2 = __vimin3_s32(t, a2, b2);
 }
 
-// Exact top-2 of one 32-column chunk: keys = ((|t|^2 - 2 q.t) << 7) | column, one IMAD each;
-// a key orders like (distance, lower column first).  Pair-sort + merge tree: 2.5 min/max per
-// element, all independent until the last levels.
-__device__ __forceinline__ void chunk_top2(const uint32_t (&r)[32], const int4* __restrict__ ck4,
-                                           int& m1, int& m2) {
-  int lo[16], hi[16];
+// Packed key of accumulator r (= q.t) and column key ck = (|t|^2 << 8) | (train row & 255):
+// ((|t|^2 - 2 q.t) << 8) | column, one IMAD; orders like (distance, lower column first).
+__device__ __forceinline__ int make_key(uint32_t r, int ck) {
+  return static_cast<int>(r) * -(2 << (kKeyShift + 1)) + ck;
+}
+
+__device__ __forceinline__ void make_keys(const uint32_t (&r)[32], const int4* __restrict__ ck4,
+                                          int (&k)[32]) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int4 cc = ck4[k];
-    const int k0 = static_cast<int>(r[4 * k + 0]) * -256 + cc.x;
-    const int k1 = static_cast<int>(r[4 * k + 1]) * -256 + cc.y;
-    const int k2 = static_cast<int>(r[4 * k + 2]) * -256 + cc.z;
-    const int k3 = static_cast<int>(r[4 * k + 3]) * -256 + cc.w;
-    lo[2 * k] = min(k0, k1);
-    hi[2 * k] = max(k0, k1);
-    lo[2 * k + 1] = min(k2, k3);
-    hi[2 * k + 1] = max(k2, k3);
+  for (int q = 0; q < 8; ++q) {
+    const int4 cc = ck4[q];
+    k[4 * q + 0] = make_key(r[4 * q + 0], cc.x);
+    k[4 * q + 1] = make_key(r[4 * q + 1], cc.y);
+    k[4 * q + 2] = make_key(r[4 * q + 2], cc.z);
+    k[4 * q + 3] = make_key(r[4 * q + 3], cc.w);
   }
+}
+
+// Exact top-2 of 8 keys merged into (m1, m2): pair-sort + merge tree, 20 min/max.
+__device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
+  int lo[4], hi[4];
 #pragma unroll
-  for (int n = 8; n >= 1; n >>= 1) {
-#pragma unroll
-    for (int j = 0; j < n; ++j) merge_top2(lo[j], hi[j], lo[j + n], hi[j + n]);
+  for (int j = 0; j < 4; ++j) {
+    lo[j] = min(k[2 * j], k[2 * j + 1]);
+    hi[j] = max(k[2 * j], k[2 * j + 1]);
   }
+  merge_top2(lo[0], hi[0], lo[2], hi[2]);
+  merge_top2(lo[1], hi[1], lo[3], hi[3]);
+  merge_top2(lo[0], hi[0], lo[1], hi[1]);
   merge_top2(m1, m2, lo[0], hi[0]);
 }
 
+// Top-2 update with the 32 keys of one chunk.
+//   kMode 0: unfiltered, every key goes through the merge tree (2.5 min/max per element).
+//   kMode 1: `thr` bounds the keys that can still enter this row's top-2 (a key >= thr has two
+//            predecessors that beat it).  Fast path: 3-input-min tree per group of 8 keys
+//            (0.5 min per element) and one warp vote; only groups in which some row of the
+//            warp beats its bound are inserted exactly (harmless for the other rows).
+template <int kMode>
+__device__ __forceinline__ void chunk_top2(const int (&k)[32], int& m1, int& m2, int& thr) {
+  if constexpr (kMode >= 2) {
+  } else if constexpr (kMode == 0) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) insert8(k + 8 * g, m1, m2);
+  } else {
+    int g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = __vimin3_s32(k[8 * j + 0], k[8 * j + 1], k[8 * j + 2]);
+      const int b = __vimin3_s32(k[8 * j + 3], k[8 * j + 4], k[8 * j + 5]);
+      g[j] = min(__vimin3_s32(a, b, k[8 * j + 6]), k[8 * j + 7]);
+    }
+    const int cmin = min(__vimin3_s32(g[0], g[1], g[2]), g[3]);
+    if (__any_sync(0xffffffffu, cmin < thr)) {
+      // the four group votes are independent (thr is only tightened afterwards)
+      const bool h0 = __any_sync(0xffffffffu, g[0] < thr);
+      const bool h1 = __any_sync(0xffffffffu, g[1] < thr);
+      const bool h2 = __any_sync(0xffffffffu, g[2] < thr);
+      const bool h3 = __any_sync(0xffffffffu, g[3] < thr);
+      if (h0) insert8(k, m1, m2);
+      if (h1) insert8(k + 8, m1, m2);
+      if (h2) insert8(k + 16, m1, m2);
+      if (h3) insert8(k + 24, m1, m2);
+      thr = min(thr, m2);
+    }
+  }
+}
+
+// lexicographic (value, index) insertion into a running top-2
+__device__ __forceinline__ void insert_vi(int v, int i, int& g1v, int& g1i, int& g2v, int& g2i) {
+  if (v < g1v || (v == g1v && i < g1i)) {
+    g2v = g1v; g2i = g1i;
+    g1v = v;   g1i = i;
+  } else if (v < g2v || (v == g2v && i < g2i)) {
+    g2v = v;   g2i = i;
+  }
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ ckey,
             const int32_t* __restrict__ norm, const PairDesc* __restrict__ pairs,
-            const int32_t* __restrict__ item_prefix, int n_pairs, int n_items,
-            Knn2* __restrict__ knn_out) {
+            const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -116,15 +182,16 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) prefetch_tensormap(&tmap);
-  if (warp == 1 && lane == 0) {
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), 2);                 // the two query halves' MMA commits
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_a_full(b), 1);
-      mbar_init(bar_a_empty(b), 1 + kEpiWarps);   // MMA commit + every epilogue warp
+      // every MMA warp + every epilogue warp
+      mbar_init(bar_a_empty(b), (dbg & 2) ? kMmaWarps : kMmaWarps + kEpiWarps);
     }
     for (int b = 0; b < kAccBufs; ++b)
       for (int h = 0; h < 2; ++h) {
@@ -133,7 +200,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
   }
@@ -141,39 +208,60 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // 768 threads leave 80 registers per thread; the control warpgroups (0: producer + idle
+  // warps, 1: MMA issuers) hand their share to the epilogue warpgroups (setmaxnreg, issued at
+  // the top of each role branch so that ptxas allocates per branch)
 
-  if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+  // Producer and MMA warps run their loops with all 32 lanes and pick the issuing lane with
+  // elect.sync: ptxas then keeps descriptors / barrier addresses in uniform registers instead
+  // of wrapping every UTCIMMA / UTMALDG in a per-thread waterfall loop (measured: 80 cycles
+  // per MMA with `if (lane == 0)`).
+  if (warp < kFirstMmaWarp) {
+    // ===================================================== TMA producer (warp 0; 1..3 idle)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+    if (warp == 0) {
       uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0, tile_seq = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        // pair of this item: last p with item_prefix[p] <= item
-        int lo = 0, hi = n_pairs;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(item_prefix + mid) <= item) lo = mid; else hi = mid;
-        }
-        const PairDesc pd = pairs[lo];
-        const int mblk = item - __ldg(item_prefix + lo);
+      int item = blockIdx.x;
+      int2 it = item < n_items ? __ldg(items + item) : make_int2(0, 0);
+      PairDesc pd = pairs[it.x];
+      for (; item < n_items; item += gridDim.x) {
+        const int mblk = it.y;
         const int ntiles = (pd.nt + kTileN - 1) / kTileN;
+        const int t_row0 = pd.t_row0;
         mbar_wait(bar_a_empty(abuf), aphase ^ 1);
-        info[abuf].ntiles = ntiles;
-        info[abuf].rows_valid = pd.nq - mblk * kTileM;
-        info[abuf].norm_row = pd.q_row0 + mblk * kTileM;
-        info[abuf].knn_row = pd.knn_off + static_cast<int64_t>(mblk) * kTileM;
-        mbar_arrive_expect_tx(bar_a_full(abuf), kABytes);
-        tma_load_2d(sA + abuf * kABytes, &tmap, bar_a_full(abuf), 0, pd.q_row0 + mblk * kTileM);
-        tma_load_2d(sA + abuf * kABytes + kAHalfBytes, &tmap, bar_a_full(abuf), 0,
-                    pd.q_row0 + mblk * kTileM + kHalfM);
+        if (elect_one()) {
+          info[abuf].ntiles = ntiles;
+          info[abuf].rows_valid = pd.nq - mblk * kTileM;
+          info[abuf].norm_row = pd.q_row0 + mblk * kTileM;
+          info[abuf].knn_row = pd.knn_off + static_cast<int64_t>(mblk) * kTileM;
+          mbar_arrive_expect_tx(bar_a_full(abuf), kABytes);
+          tma_load_2d(sA + abuf * kABytes, &tmap, bar_a_full(abuf), 0, pd.q_row0 + mblk * kTileM);
+          tma_load_2d(sA + abuf * kABytes + kAHalfBytes, &tmap, bar_a_full(abuf), 0,
+                      pd.q_row0 + mblk * kTileM + kHalfM);
+        }
+        __syncwarp();
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1;
+        // fetch the next item's tables now; the loads land while this item's tiles stream
+        const int nxt = item + gridDim.x;
+        if (nxt < n_items) {
+          it = __ldg(items + nxt);
+          pd = pairs[it.x];
+        }
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes);
-          const int row = pd.t_row0 + t * kTileN;
-          tma_load_2d(sB + stage * kBBytes, &tmap, bar_full(stage), 0, row);
-          bulk_load_1d(sCk + (tile_seq % kCkSlots) * kCkBytes, ckey + row, kCkBytes,
-                       bar_full(stage));
+          const int row = t_row0 + t * kTileN;
+          if (elect_one()) {
+            if (dbg & 1) {                       // timing experiment: no operand traffic
+              mbar_arrive(bar_full(stage));
+            } else {
+              mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes);
+              tma_load_2d(sB + stage * kBBytes, &tmap, bar_full(stage), 0, row);
+              bulk_load_1d(sCk + (tile_seq % kCkSlots) * kCkBytes, ckey + row, kCkBytes,
+                           bar_full(stage));
+            }
+          }
+          __syncwarp();
           ++tile_seq;
           if (++stage == kStages) {
             stage = 0;
@@ -182,58 +270,65 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_u8(kHalfM, kTileN);
-      uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0, buf = 0, bphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(bar_a_full(abuf), aphase);
-        const int ntiles = info[abuf].ntiles;
-        const uint64_t a_desc0 = make_smem_desc_sw128(sA + abuf * kABytes);
-        const uint64_t a_desc1 = make_smem_desc_sw128(sA + abuf * kABytes + kAHalfBytes);
-        for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(bar_full(stage), phase);
-          const uint64_t b_desc = make_smem_desc_sw128(sB + stage * kBBytes);
+  } else if (warp >= kFirstMmaWarp && warp < kFirstEpiWarp) {
+    // ===================================================== MMA issuers: (half mh, parity mp)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+    const int mh = (warp - kFirstMmaWarp) & 1, mp = (warp - kFirstMmaWarp) >> 1;
+    constexpr uint32_t idesc = make_idesc_u8(kHalfM, kTileN);
+    const uint32_t d_tmem = tmem_base + mp * (2 * kTileN) + mh * kTileN;
+    uint32_t seq = 0, abuf = 0, aphase = 0;     // seq = tiles of this CTA so far
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      mbar_wait(bar_a_full(abuf), aphase);
+      const int ntiles = info[abuf].ntiles;
+      const uint64_t a_desc = make_smem_desc_sw128(sA + abuf * kABytes + mh * kAHalfBytes);
+      bool own_any = false;
+      for (int t = 0; t < ntiles; ++t, ++seq) {
+        if ((seq & 1) != static_cast<uint32_t>(mp)) continue;
+        own_any = true;
+        const uint32_t stage = seq % kStages, phase = (seq / kStages) & 1;
+        mbar_wait(bar_full(stage), phase);
+        if (!(dbg & 2)) mbar_wait(bar_t_empty(mp, mh), ((seq >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t b_desc = make_smem_desc_sw128(sB + stage * kBBytes);
+        if (elect_one()) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(bar_t_empty(buf, h), bphase ^ 1);
-            tc_fence_after();
-            const uint32_t d = tmem_base + buf * (2 * kTileN) + h * kTileN;
-            const uint64_t a_desc = h ? a_desc1 : a_desc0;
-#pragma unroll
-            for (int k = 0; k < kDim / 32; ++k) {
-              // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4)
-              umma_i8(d, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
-            }
-            umma_commit(bar_t_full(buf, h));
+          for (int k = 0; k < kDim / 32; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4)
+            umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
           }
+          umma_commit(bar_t_full(mp, mh));
           umma_commit(bar_empty(stage));
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-          if (++buf == kAccBufs) {
-            buf = 0;
-            bphase ^= 1;
-          }
+          if (t + 2 >= ntiles) umma_commit(bar_a_empty(abuf));   // this warp's last tile
         }
-        umma_commit(bar_a_empty(abuf));
-        abuf ^= 1;
-        if (abuf == 0) aphase ^= 1;
+        __syncwarp();
       }
+      if (!own_any) {                            // single-tile item of the other parity
+        if (elect_one()) mbar_arrive(bar_a_empty(abuf));
+        __syncwarp();
+      }
+      abuf ^= 1;
+      if (abuf == 0) aphase ^= 1;
     }
   } else if (warp >= kFirstEpiWarp) {
     // ===================================================== epilogue: running top-2 per row
-    const int half = (warp - kFirstEpiWarp) >> 2;  // which 128-row half of the block
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    const int e = warp - kFirstEpiWarp;            // 4 consecutive warps cover the 4 quarters
+    const int half = e >> 3;                       // which 128-row half of the block
+    const int chalf = (e >> 2) & 1;                // which 64-column half of every tile
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row_in_blk = half * kHalfM + quarter * 32 + lane;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * kTileN;
-    uint32_t buf = 0, bphase = 0, tile_seq = 0, abuf = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int g1v = INT32_MAX, g2v = INT32_MAX, g1i = -1, g2i = -1;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                            half * kTileN + chalf * kColsPerThread;
+    int4* merge_buf = reinterpret_cast<int4*>(smem_gen + kOffMerge);
+    const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
+    uint32_t buf = 0, bphase = 0, tile_seq = 0, abuf = 0, mslot = 0;
+    for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
+      int g1v = INT32_MAX, g2v = INT32_MAX, g1i = INT32_MAX, g2i = INT32_MAX;
       int ntiles = 1, rows_valid = 0, norm_row = 0;
       int64_t knn_row = 0;
+      // window-local top-2 as packed keys; a window is a pair of train tiles (256 columns,
+      // the 8 column bits of a key); thr = bound on keys that can still enter the top-2
+      int m1 = INT32_MAX, m2 = INT32_MAX, thr = INT32_MAX;
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(bar_t_full(buf, half), bphase);
         tc_fence_after();
@@ -247,39 +342,76 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           abuf ^= 1;
         }
         const int4* ck4 = reinterpret_cast<const int4*>(smem_gen + kOffCk +
-                                                        (tile_seq % kCkSlots) * kCkBytes);
-        int m1 = INT32_MAX, m2 = INT32_MAX;
+                                                        (tile_seq % kCkSlots) * kCkBytes) +
+                          chalf * (kColsPerThread / 4);
         const uint32_t ta = t_addr + buf * (2 * kTileN);
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld_x32(ta, r0);
-          tmem_ld_x32(ta + 32, r1);
+        if constexpr (kMode >= 2) {
+          // timing experiments only (results are garbage): 2 = drain TMEM, 3 = handshake only
+          if constexpr (kMode == 4) {
+            // fast path of a raw-accumulator filter: 3-input max tree per 8 columns + compare
+            uint32_t r[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld_x32(ta + 32 * c, r);
+              tmem_ld_wait();
+              int gm[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
+                const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
+                gm[j] = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (gm[j] > thr) { m1 = gm[j]; ++m2; }       // stands in for a predicated append
+            }
+          }
+          if constexpr (kMode == 2) {
+            uint32_t r[32];
+            tmem_ld_x32(ta, r);
+            tmem_ld_wait();
+            m1 = min(m1, static_cast<int>(r[0] ^ r[31]));
+            tmem_ld_x32(ta + 32, r);
+            tmem_ld_wait();
+            m2 = min(m2, static_cast<int>(r[0] ^ r[31]));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
+        } else {
+          uint32_t r[32];
+          int k[32];
+          tmem_ld_x32(ta, r);
           tmem_ld_wait();
-          chunk_top2(r0, ck4, m1, m2);
-          tmem_ld_x32(ta + 64, r0);
-          chunk_top2(r1, ck4 + 8, m1, m2);
+          make_keys(r, ck4, k);
+          tmem_ld_x32(ta + 32, r);          // in flight while the first chunk is filtered
+          chunk_top2<kMode>(k, m1, m2, thr);
           tmem_ld_wait();
-          tmem_ld_x32(ta + 96, r1);
-          chunk_top2(r0, ck4 + 16, m1, m2);
-          tmem_ld_wait();
-          chunk_top2(r1, ck4 + 24, m1, m2);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));   // TMEM reads of this tile done
+          make_keys(r, ck4 + 8, k);
+          chunk_top2<kMode>(k, m1, m2, thr);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-        // merge the tile's top-2 into the running (value, index) pairs; later tiles hold
-        // larger indices, so strict '<' keeps the lower index on equal distance.
-        const int base = t * kTileN;
-        const int v1 = m1 >> 7, i1 = base + (m1 & 127);
-        const int v2 = m2 >> 7, i2 = base + (m2 & 127);
-        if (v1 < g1v) {
-          g2v = g1v; g2i = g1i;
-          g1v = v1;  g1i = i1;
-        } else if (v1 < g2v) {
-          g2v = v1;  g2i = i1;
-        }
-        if (v2 < g2v) {
-          g2v = v2;  g2i = i2;
+        if ((t & 1) || t == ntiles - 1) {
+          // merge the window's top-2 into the running (value, index) pairs; later windows
+          // hold larger indices, so strict '<' keeps the lower index on equal distance.
+          const int base = (t & ~1) * kTileN;
+          const int v1 = m1 >> (kKeyShift + 1), i1 = base + (m1 & (2 * kTileN - 1));
+          const int v2 = m2 >> (kKeyShift + 1), i2 = base + (m2 & (2 * kTileN - 1));
+          if (v1 < g1v) {
+            g2v = g1v; g2i = g1i;
+            g1v = v1;  g1i = i1;
+          } else if (v1 < g2v) {
+            g2v = v1;  g2i = i1;
+          }
+          if (v2 < g2v) {
+            g2v = v2;  g2i = i2;
+          }
+          m1 = INT32_MAX;
+          m2 = INT32_MAX;
+          // key < (g2v << 8)  <=>  value < g2v
+          thr = g2v < (1 << 22) ? g2v << (kKeyShift + 1) : INT32_MAX;
         }
         ++tile_seq;
         if (++buf == kAccBufs) {
@@ -287,21 +419,32 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           bphase ^= 1;
         }
       }
-      if (row_in_blk < rows_valid) {
-        const int nq2 = __ldg(norm + norm_row + row_in_blk);
-        Knn2 out;
-        out.j0 = g1i;
-        out.j1 = g2i;
-        out.d0 = g1v + nq2;
-        out.d1 = g2v + nq2;
-        *reinterpret_cast<int4*>(&knn_out[knn_row + row_in_blk]) = *reinterpret_cast<int4*>(&out);
+      // merge the two column halves of the row: the upper half hands its top-2 over
+      int4* slot = merge_buf + mslot * kTileM + row_in_blk;
+      mslot ^= 1;
+      if (chalf == 1) *slot = make_int4(g1v, g1i, g2v, g2i);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (chalf == 0) {
+        const int4 o = *slot;
+        insert_vi(o.x, o.y, g1v, g1i, g2v, g2i);
+        insert_vi(o.z, o.w, g1v, g1i, g2v, g2i);
+        if (row_in_blk < rows_valid) {
+          const int nq2 = __ldg(norm + norm_row + row_in_blk);
+          Knn2 out;
+          out.j0 = g1i;
+          out.j1 = g2i;
+          out.d0 = g1v + nq2;
+          out.d1 = g2v + nq2;
+          *reinterpret_cast<int4*>(&knn_out[knn_row + row_in_blk]) =
+              *reinterpret_cast<int4*>(&out);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kFirstMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -311,7 +454,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
 // Bare tensor-pipe probe: back-to-back 128x256x32 u8 MMAs on every SM, operands resident
 // in shared memory (contents irrelevant), no epilogue.  Gives the measured int8 peak.
 constexpr uint32_t kProbeA = 128 * kDim, kProbeB = 256 * kDim;
-__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
+// variant (timing experiments on the single issuing thread, N = 128 only):
+//   0 MMAs only   1 + tcgen05.commit every 4 MMAs   2 + commit every 8 MMAs
+//   3 + commit every 8 and a try_wait on a completed mbarrier every 8 MMAs
+//   4 two issuing threads (warps 0 and 2), each half of the MMAs, commit every 4
+template <int kN>
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int variant) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -322,9 +470,14 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < (kProbeA + kProbeB) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem_gen)[i] = 0x01010101u * (i & 3);
+  const uint32_t bar_dummy = bar + 32, bar_done = bar + 40, bar2 = bar + 48;
   if (warp == 0 && lane == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar_dummy, 0x7fff);     // never completes: sink for experiment commits
+    mbar_init(bar_done, 1);
+    mbar_init(bar2, 1);
     fence_mbar_init();
+    mbar_arrive(bar_done);            // phase 0 complete: try_wait(parity 0) succeeds at once
   }
   if (warp == 1) {
     tmem_alloc(smem_base + kProbeA + kProbeB + 16, 512);
@@ -335,16 +488,38 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  if (warp == 0 && lane == 0) {
-    constexpr uint32_t idesc = make_idesc_u8(128, 256);
+  if (warp == 0) {
+    // whole warp runs the loop; elect.sync picks the issuing lane, which lets ptxas keep the
+    // descriptors in uniform registers without a per-instruction waterfall loop
+    constexpr uint32_t idesc = make_idesc_u8(128, kN);
+    const uint64_t a_desc = make_smem_desc_sw128(sA), b_desc = make_smem_desc_sw128(sB);
+    const int n = variant == 4 ? iters : iters * (256 / kN);
+    for (int i = 0; i < n; ++i) {
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_i8(tmem_base + (i & 1) * 256, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+        if (variant == 1 || variant == 4) umma_commit(bar_dummy);
+        if ((variant == 2 || variant == 3) && (i & 1)) umma_commit(bar_dummy);
+      }
+      __syncwarp();
+      if (variant == 3 && (i & 1)) mbar_wait(bar_done, 0);
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    mbar_wait(bar, 0);
+  }
+  if (variant == 4 && warp == 2 && lane == 0) {
+    constexpr uint32_t idesc = make_idesc_u8(128, kN);
     const uint64_t a_desc = make_smem_desc_sw128(sA), b_desc = make_smem_desc_sw128(sB);
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_i8(tmem_base + (i & 1) * 256, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+        umma_i8(tmem_base + 128 + (i & 1) * 256, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+      umma_commit(bar_dummy);
     }
-    umma_commit(bar);
-    mbar_wait(bar, 0);
+    umma_commit(bar2);
+    mbar_wait(bar2, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -357,29 +532,62 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
 // -------------------------------------------------------------------------------------
 // host-side launchers (called from capi.cu)
 
-cudaError_t launch_knn2(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* norm,
-                        const PairDesc* pairs, const int32_t* item_prefix, int n_pairs,
+// mode 0: unfiltered exact top-2 epilogue; mode 1: threshold-filtered (default, same results)
+cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
+                        const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream) {
+  const int dbg = mode >> 4;   // timing experiments (results invalid), see tools/exp_modes.py
+  mode &= 15;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kKnnSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(knn2_kernel<0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kKnnSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(knn2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kKnnSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(knn2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kKnnSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(knn2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kKnnSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
-  knn2_kernel<<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, item_prefix,
-                                                            n_pairs, n_items, knn_out);
+  if (mode == 4)
+    knn2_kernel<4><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+                                                                 n_items, knn_out, dbg);
+  else if (mode == 2)
+    knn2_kernel<2><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+                                                                 n_items, knn_out, dbg);
+  else if (mode == 3)
+    knn2_kernel<3><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+                                                                 n_items, knn_out, dbg);
+  else if (mode == 0)
+    knn2_kernel<0><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+                                                                 n_items, knn_out, dbg);
+  else
+    knn2_kernel<1><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+                                                                 n_items, knn_out, dbg);
   return cudaGetLastError();
 }
 
+// iters > 0: 128x256x32 MMAs; iters < 0: -(n << 4 | variant): the same work as 128x128x32
+// MMAs with the issue-thread experiment `variant` (see i8_peak_kernel)
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream) {
   const uint32_t smem = kProbeA + kProbeB + 64 + 1024;
-  cudaError_t e =
-      cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(i8_peak_kernel<256>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  i8_peak_kernel<<<n_sms, 128, smem, stream>>>(iters);
+  e = cudaFuncSetAttribute(i8_peak_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  if (iters > 0) i8_peak_kernel<256><<<n_sms, 128, smem, stream>>>(iters, 0);
+  else i8_peak_kernel<128><<<n_sms, 128, smem, stream>>>((-iters) >> 4, (-iters) & 15);
   return cudaGetLastError();
 }
 

@@ -7,7 +7,7 @@ namespace sfm {
 constexpr int kDim = 128;          // SIFT descriptor length in bytes (u8)
 constexpr int kTileM = 256;        // query rows per work item (two 128-lane TMEM halves)
 constexpr int kTileN = 128;        // train rows per B tile (TMEM columns per half)
-constexpr int kKeyShift = 7;       // packed key = (|t|^2 - 2 q.t) << 7 | (train row & 127)
+constexpr int kKeyShift = 7;       // log2(kTileN); packed key = (|t|^2 - 2 q.t) << 8 | (train row & 255)
 constexpr int kRowPad = 256;       // every image is padded to a multiple of this many rows
 constexpr int kNormPad = 0x7FFFFF; // norm^2 sentinel of padding rows (never selected)
 

@@ -193,3 +193,23 @@ def test_capacity_error_reports_need(ctx):
                              pt.ctypes.data_as(C.POINTER(C.c_int32)), 1, 0.6, 10.0, 5.0,
                              out.ctypes.data, 1, off.ctypes.data_as(C.POINTER(C.c_int64)), None, None)
     assert rc == -8 and off[1] == need
+
+
+def test_filtered_epilogue_equals_unfiltered(ctx, monkeypatch):
+    """SFM_KNN_MODE=0 runs the unfiltered exact top-2 epilogue; the default threshold-filtered
+    epilogue must give identical raw kNN rows and match lists."""
+    import sfm_opencv_b200 as sfm
+    bank = synth.image_bank(3, 3000, seed0=80)
+    bank[2][100:140] = bank[0][5]                    # many equal distances
+    pairs = [(0, 1), (1, 2), (0, 2), (2, 0)]
+    ctx.upload_descriptors(bank)
+    m1, md1, k1 = ctx.match_pairs(pairs, want_knn=True)
+    monkeypatch.setenv("SFM_KNN_MODE", "0")
+    with sfm.Context(0) as c0:
+        c0.upload_descriptors(bank)
+        m0, md0, k0 = c0.match_pairs(pairs, want_knn=True)
+    for a, b in zip(k0, k1):
+        assert np.array_equal(a, b)
+    for a, b in zip(m0, m1):
+        assert np.array_equal(a, b)
+    assert np.array_equal(_bits(md0), _bits(md1))
