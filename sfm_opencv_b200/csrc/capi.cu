@@ -21,7 +21,8 @@ cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 // match_finalize.cu
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
-                             int32_t* norm, int32_t* ckey, uint32_t* flags, cudaStream_t s);
+                             int32_t* norm, int32_t* ckey, uint32_t* flags, int32_t* min_norm,
+                             cudaStream_t s);
 cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
                           float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
                           int64_t* offsets, cudaStream_t s);
@@ -87,7 +88,8 @@ struct sfm_ctx {
   EncodeTiledFn encode = nullptr;
 
   // descriptor bank (padded rows)
-  DevBuf desc, norm, ckey, flags, stage;
+  DevBuf desc, norm, ckey, flags, stage, img_min;   // img_min: min |row|^2 per image
+  std::vector<int32_t> img_min_norm;
   std::vector<int32_t> img_n, img_row0;
   std::vector<int2> h_items;                   // reused host staging of the work-item table
   int64_t bank_rows = 0;
@@ -192,7 +194,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->flags, &ctx->stage, &ctx->pairs,
+  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
                     &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
@@ -276,7 +278,8 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
     ctx->img_row0[i] = static_cast<int32_t>(rows);
     rows += (static_cast<int64_t>(n_desc[i]) + kRowPad - 1) / kRowPad * kRowPad;
     if (n_desc[i] > max_n) max_n = n_desc[i];
-    if (rows > INT32_MAX - kRowPad) return fail(ctx, SFM_E_INVALID, "descriptor bank too large");
+    if (rows >= (1 << 26) - kRowPad)   // kernel packs (bank row | lane << 26) into one word
+      return fail(ctx, SFM_E_INVALID, "descriptor bank too large (2^26 rows)");
   }
   if (rows == 0) rows = kRowPad;
   ctx->bank_rows = rows;
@@ -284,6 +287,8 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   CK(ctx->norm.ensure(static_cast<size_t>(rows) * 4));
   CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
   CK(ctx->flags.ensure(4));
+  CK(ctx->img_min.ensure(4 * static_cast<size_t>(n_img)));
+  CK(cudaMemsetAsync(ctx->img_min.p, 0x7f, 4 * static_cast<size_t>(n_img), ctx->stream));
   const size_t elt = f32 ? 4 : 1;
   const size_t img_bytes = static_cast<size_t>(max_n) * kDim * elt;
   CK(ctx->stage.ensure(2 * img_bytes + 512));
@@ -296,10 +301,13 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
     if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_pack_rows(f32, st, n_desc[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
                         ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(),
-                        ctx->flags.as<uint32_t>(), ctx->stream));
+                        ctx->flags.as<uint32_t>(), ctx->img_min.as<int32_t>() + i, ctx->stream));
     ctx->launches += 2;
   }
   uint32_t flags = 0;
+  ctx->img_min_norm.assign(n_img, 0);
+  CK(cudaMemcpyAsync(ctx->img_min_norm.data(), ctx->img_min.p, 4 * static_cast<size_t>(n_img),
+                     cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (flags & 2u) return fail(ctx, SFM_E_RANGE, "descriptor value outside 0..255");
@@ -352,6 +360,8 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     pd.t_row0 = ctx->img_row0[t];
     pd.nq = ctx->img_n[q];
     pd.nt = ctx->img_n[t];
+    pd.nt_min = ctx->img_min_norm[t];
+    pd.pad = 0;
     pd.knn_off = rows;
     rows += pd.nq;
     const int mb = (pd.nq + kTileM - 1) / kTileM;

@@ -25,7 +25,8 @@ constexpr int kMaxNorm = (1 << 21) - 1;
 template <bool kF32>
 __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
                                  uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
-                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags) {
+                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags,
+                                 int32_t* __restrict__ min_norm) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -52,6 +53,7 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (s > kMaxNorm) bad |= kFlagNorm;
   if (lane == 0) {
+    atomicMin(min_norm, s);
     norm[row0 + r] = s;
     ckey[row0 + r] = (s << (kKeyShift + 1)) | (r & (2 * kTileN - 1));
   }
@@ -221,14 +223,17 @@ __global__ void knn_to_float_kernel(const Knn2* __restrict__ knn, int64_t n,
 
 // ------------------------------------------------------------------------------- launchers
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
-                             int32_t* norm, int32_t* ckey, uint32_t* flags, cudaStream_t s) {
+                             int32_t* norm, int32_t* ckey, uint32_t* flags, int32_t* min_norm,
+                             cudaStream_t s) {
   if (n > 0) {
     const int warps = 8;
     const int grid = (n + warps - 1) / warps;
     if (f32)
-      pack_rows_kernel<true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
+      pack_rows_kernel<true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags,
+                                                         min_norm);
     else
-      pack_rows_kernel<false><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
+      pack_rows_kernel<false><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags,
+                                                          min_norm);
   }
   const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
   if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 255) / 256, 256, 0, s>>>(n, n_pad, row0, norm, ckey);

@@ -6,20 +6,34 @@
 // d2(i,j) = |q_i|^2 + |t_j|^2 - 2 q_i.t_j with q.t from tcgen05.mma.kind::i8 (u8 x u8 -> s32,
 // exact).  One persistent CTA per SM; a work item is a 256-row query block of one image pair,
 // swept over all 128-row train tiles of the pair:
-//   warp 0       TMA producer : the 256-row A block once per item (2 x 16 KB), B tiles
-//                               (128 train rows, 16 KB) + their column keys through a ring
+//   warp 0       TMA producer : the 256-row A block once per item (2 x 16 KB) and the train
+//                               image as 128-row B tiles (16 KB) through an mbarrier ring
 //   warps 4..7   MMA issuers  : warp (h, p) issues the 4 MMAs (128x128x32) of query half h for
 //                               the tiles of parity p into TMEM accumulator [p][h]; every B
 //                               byte feeds 256 query rows.  Four issuers because a
 //                               tcgen05.mma / commit / mbarrier wait each stall the issuing
 //                               thread for 50-100 cycles (measured, tools/exp_probe.py): one
-//                               thread cannot keep the tensor pipe busy at 64 cycles per MMA
+//                               thread cannot keep the tensor pipe busy at 64 cycles per MMA.
+//                               One warp per accumulator, in order: parity waits on its
+//                               full/empty mbarriers must never be two phases early
 //                               (512 TMEM columns = 2 buffers x 2 halves x 128)
 //   warps 8..23  epilogue     : 16 warps = 2 query halves x 2 column halves x 4 TMEM lane
 //                               quarters; a thread owns one query row and 64 of the 128
-//                               columns of every tile: tcgen05.ld, packed (distance,index)
-//                               keys, threshold-filtered exact top-2; the two column halves of
-//                               a row are merged once per item through shared memory
+//                               columns of every tile.
+//
+// Epilogue = exact running top-2 per row, organised around the measured budget of ~1 ALU
+// op per accumulator (tools/ubench.cu): the fast path looks only at RAW dot products.
+// A column j can enter a row's top-2 only if |t_j|^2 - 2 q.t_j < v2 (v2 = second-best value so
+// far), hence only if q.t_j > (min_j |t_j|^2 - v2) / 2 =: thr.  Per group of 8 columns: a
+// 3-input-max tree (0.5 op/element) and one compare against the row's thr.  Groups that pass
+// (~2 ln(n) per row and sweep) are appended -- raw accumulators + (bank row, owner lane) -- to
+// a per-warp queue in shared memory.  The queue is drained cooperatively: lane L rebuilds
+// the exact packed keys of event L from the column keys in global memory, takes their top-2
+// and mails it to the owner lane, which merges it into its running (value, index) pairs with
+// a lexicographic insert, then tightens thr.  The first two tiles of a sweep and any chunk
+// that would overflow the queue take the unfiltered exact path.  Skipped columns provably
+// have two predecessors that beat them, so results are identical to the unfiltered epilogue
+// (SFM_KNN_MODE=0); a GPU test compares the two bit for bit.
 // The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -33,42 +47,55 @@ namespace sfm {
 
 constexpr int kStages = 6;                      // B-tile ring depth (16 KB each)
 constexpr int kAccBufs = 2;                     // TMEM accumulator buffers (2 x 128 columns each)
-constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
 constexpr int kFirstMmaWarp = 4;                // warps 1..3 idle (warpgroup granularity)
 constexpr int kMmaWarps = 4;                    // (query half, tile parity)
 constexpr int kFirstEpiWarp = kFirstMmaWarp + kMmaWarps;
-constexpr int kRegsCtl = 48;                    // setmaxnreg: producer / MMA warpgroups
+constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
+constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;       // 768
+constexpr int kRegsCtl = 40;                    // setmaxnreg: producer / MMA warpgroups
 constexpr int kRegsEpi = 96;                    // setmaxnreg: epilogue warpgroups
 static_assert(8 * kRegsCtl + 16 * kRegsEpi <= 24 * 80, "register pool of the CTA (768 x 80)");
-constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
-constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
+constexpr int kExactTiles = 2;                  // tiles at the start of a sweep done unfiltered
+constexpr int kQueueSlots = 32;                 // events per warp queue (one per lane to drain)
+constexpr int kFlushAt = 20;                    // drain when this many events are queued
+constexpr int kRowBits = 26;                    // bank rows < 2^26 (event meta = row | lane << 26)
 
 constexpr uint32_t kABytes = kTileM * kDim;     // 32 KB
 constexpr uint32_t kAHalfBytes = kHalfM * kDim; // 16 KB
 constexpr uint32_t kBBytes = kTileN * kDim;     // 16 KB
-constexpr uint32_t kCkBytes = kTileN * 4;       // 512 B
 
 // What the producer tells the MMA and epilogue warps about an item.
 struct ItemInfo {
   int32_t ntiles;       // train tiles of the pair
   int32_t rows_valid;   // query rows of this block that exist (<= 256)
   int32_t norm_row;     // bank row of the block's first query row
+  int32_t t_row0;       // bank row of the train image's first row
+  int32_t nt_min;       // min |t|^2 over the train image
   int32_t pad;
   int64_t knn_row;      // first output row of the block
 };
 
+// per epilogue warp: event queue + mailboxes (byte offsets inside the warp's block)
+constexpr uint32_t kQAcc = 0;                              // [32 slots][8] raw accumulators
+constexpr uint32_t kQMeta = kQAcc + kQueueSlots * 32;      // [32] bank row | owner lane << 26
+constexpr uint32_t kQMail = kQMeta + kQueueSlots * 4;      // [32 lanes] (v1, i1, v2, i2)
+constexpr uint32_t kQCount = kQMail + 32 * 16;             // events queued
+constexpr uint32_t kQBytes = kQCount + 16;
+
 // dynamic shared memory map (offsets from a 1024-byte aligned base)
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + 2 * kABytes;
-constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
-constexpr uint32_t kOffInfo = kOffCk + kCkSlots * kCkBytes;
+constexpr uint32_t kOffInfo = kOffB + kStages * kBBytes;
 constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
-constexpr uint32_t kOffBar = kOffMerge + 2 * kTileM * 16;
+constexpr uint32_t kOffQueue = kOffMerge + 2 * kTileM * 16;
+constexpr uint32_t kOffBar = kOffQueue + kEpiWarps * kQBytes;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kKnnSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
+static_assert(kKnnSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(sizeof(ItemInfo) == 32 && kQBytes % 16 == 0, "smem layout");
 
 // (a1 <= a2), (b1 <= b2) -> the two smallest of the four, sorted.
 __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
@@ -81,18 +108,6 @@ __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
 // ((|t|^2 - 2 q.t) << 8) | column, one IMAD; orders like (distance, lower column first).
 __device__ __forceinline__ int make_key(uint32_t r, int ck) {
   return static_cast<int>(r) * -(2 << (kKeyShift + 1)) + ck;
-}
-
-__device__ __forceinline__ void make_keys(const uint32_t (&r)[32], const int4* __restrict__ ck4,
-                                          int (&k)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int4 cc = ck4[q];
-    k[4 * q + 0] = make_key(r[4 * q + 0], cc.x);
-    k[4 * q + 1] = make_key(r[4 * q + 1], cc.y);
-    k[4 * q + 2] = make_key(r[4 * q + 2], cc.z);
-    k[4 * q + 3] = make_key(r[4 * q + 3], cc.w);
-  }
 }
 
 // Exact top-2 of 8 keys merged into (m1, m2): pair-sort + merge tree, 20 min/max.
@@ -109,49 +124,137 @@ __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
   merge_top2(m1, m2, lo[0], hi[0]);
 }
 
-// Top-2 update with the 32 keys of one chunk.
-//   kMode 0: unfiltered, every key goes through the merge tree (2.5 min/max per element).
-//   kMode 1: `thr` bounds the keys that can still enter this row's top-2 (a key >= thr has two
-//            predecessors that beat it).  Fast path: 3-input-min tree per group of 8 keys
-//            (0.5 min per element) and one warp vote; only groups in which some row of the
-//            warp beats its bound are inserted exactly (harmless for the other rows).
-template <int kMode>
-__device__ __forceinline__ void chunk_top2(const int (&k)[32], int& m1, int& m2, int& thr) {
-  if constexpr (kMode >= 2) {
-  } else if constexpr (kMode == 0) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) insert8(k + 8 * g, m1, m2);
-  } else {
-    int g[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = __vimin3_s32(k[8 * j + 0], k[8 * j + 1], k[8 * j + 2]);
-      const int b = __vimin3_s32(k[8 * j + 3], k[8 * j + 4], k[8 * j + 5]);
-      g[j] = min(__vimin3_s32(a, b, k[8 * j + 6]), k[8 * j + 7]);
-    }
-    const int cmin = min(__vimin3_s32(g[0], g[1], g[2]), g[3]);
-    if (__any_sync(0xffffffffu, cmin < thr)) {
-      // the four group votes are independent (thr is only tightened afterwards)
-      const bool h0 = __any_sync(0xffffffffu, g[0] < thr);
-      const bool h1 = __any_sync(0xffffffffu, g[1] < thr);
-      const bool h2 = __any_sync(0xffffffffu, g[2] < thr);
-      const bool h3 = __any_sync(0xffffffffu, g[3] < thr);
-      if (h0) insert8(k, m1, m2);
-      if (h1) insert8(k + 8, m1, m2);
-      if (h2) insert8(k + 16, m1, m2);
-      if (h3) insert8(k + 24, m1, m2);
-      thr = min(thr, m2);
-    }
-  }
+// top-2 (as packed keys) of the 8 columns starting at bank row `row`, accumulators a[0..7]
+__device__ __forceinline__ void group_top2(const uint32_t* a, const int32_t* __restrict__ ckey,
+                                           int row, int& e1, int& e2) {
+  const int4 c0 = __ldg(reinterpret_cast<const int4*>(ckey + row));
+  const int4 c1 = __ldg(reinterpret_cast<const int4*>(ckey + row) + 1);
+  int k[8];
+  k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
+  k[2] = make_key(a[2], c0.z); k[3] = make_key(a[3], c0.w);
+  k[4] = make_key(a[4], c1.x); k[5] = make_key(a[5], c1.y);
+  k[6] = make_key(a[6], c1.z); k[7] = make_key(a[7], c1.w);
+  insert8(k, e1, e2);
 }
 
-// lexicographic (value, index) insertion into a running top-2
-__device__ __forceinline__ void insert_vi(int v, int i, int& g1v, int& g1i, int& g2v, int& g2i) {
-  if (v < g1v || (v == g1v && i < g1i)) {
-    g2v = g1v; g2i = g1i;
-    g1v = v;   g1i = i;
-  } else if (v < g2v || (v == g2v && i < g2i)) {
-    g2v = v;   g2i = i;
+// Running state of one epilogue thread (one query row, half of the columns).
+struct RowTop2 {
+  int g1v, g1i, g2v, g2i;   // best / second best: value = |t|^2 - 2 q.t, index in the train image
+  int thr;                  // q.t must exceed this to matter: (nt_min - g2v) >> 1
+};
+
+__device__ __forceinline__ bool lex_lt(int v, int i, int gv, int gi) {
+  return (v < gv) | ((v == gv) & (i < gi));
+}
+
+// lexicographic (value, index) insertion into the running top-2: order independent,
+// branch free; (INT32_MAX, INT32_MAX) is a no-op
+__device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
+  const bool b1 = lex_lt(v, i, s.g1v, s.g1i);
+  const bool b2 = lex_lt(v, i, s.g2v, s.g2i);
+  s.g2v = b1 ? s.g1v : (b2 ? v : s.g2v);
+  s.g2i = b1 ? s.g1i : (b2 ? i : s.g2i);
+  s.g1v = b1 ? v : s.g1v;
+  s.g1i = b1 ? i : s.g1i;
+}
+
+__device__ __forceinline__ void update_thr(RowTop2& s, int nt_min) {
+  s.thr = s.g2v < (1 << 22) ? (nt_min - s.g2v) >> 1 : -1;
+}
+
+// Unfiltered exact update with the 32 columns of one chunk (bank rows crow.., indices cidx..).
+__device__ __forceinline__ void chunk_exact(const uint32_t (&r)[32],
+                                            const int32_t* __restrict__ ckey, int crow, int cidx,
+                                            RowTop2& s) {
+  int e1 = INT32_MAX, e2 = INT32_MAX;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) group_top2(&r[8 * g], ckey, crow + 8 * g, e1, e2);
+  const int base = cidx & ~(2 * kTileN - 1);     // packed keys carry 8 column bits
+  insert_vi(s, e1 >> (kKeyShift + 1), base + (e1 & (2 * kTileN - 1)));
+  insert_vi(s, e2 >> (kKeyShift + 1), base + (e2 & (2 * kTileN - 1)));
+}
+
+// Cooperative drain of the warp queue at shared address qa (n events, n <= 32): lane L
+// rebuilds the exact keys of event L, drops what can no longer enter the owner's top-2 and
+// mails the rest to the owner lane, one event per owner and round.
+__device__ __forceinline__ void queue_flush(uint32_t qa, int n, int lane,
+                                            const int32_t* __restrict__ ckey, int t_row0,
+                                            int nt_min, RowTop2& s) {
+  int v1 = INT32_MAX, i1 = INT32_MAX, v2 = INT32_MAX, i2 = INT32_MAX;
+  uint32_t owner = lane;
+  if (lane < n) {
+    const uint32_t meta = static_cast<uint32_t>(lds_32(qa + kQMeta + lane * 4));
+    const int row = static_cast<int>(meta & ((1u << kRowBits) - 1));
+    owner = meta >> kRowBits;
+    const int4 a0 = lds_v4(qa + kQAcc + lane * 32), a1 = lds_v4(qa + kQAcc + lane * 32 + 16);
+    const uint32_t a[8] = {static_cast<uint32_t>(a0.x), static_cast<uint32_t>(a0.y),
+                           static_cast<uint32_t>(a0.z), static_cast<uint32_t>(a0.w),
+                           static_cast<uint32_t>(a1.x), static_cast<uint32_t>(a1.y),
+                           static_cast<uint32_t>(a1.z), static_cast<uint32_t>(a1.w)};
+    int e1 = INT32_MAX, e2 = INT32_MAX;
+    group_top2(a, ckey, row, e1, e2);
+    const int base = (row - t_row0) & ~(2 * kTileN - 1);
+    v1 = e1 >> (kKeyShift + 1); i1 = base + (e1 & (2 * kTileN - 1));
+    v2 = e2 >> (kKeyShift + 1); i2 = base + (e2 & (2 * kTileN - 1));
+  }
+  // the owner's current second best: anything not below it cannot enter any more
+  const int ov = __shfl_sync(0xffffffffu, s.g2v, owner);
+  const int oi = __shfl_sync(0xffffffffu, s.g2i, owner);
+  const bool c1 = lex_lt(v1, i1, ov, oi);          // false for lanes without an event
+  if (!lex_lt(v2, i2, ov, oi)) { v2 = INT32_MAX; i2 = INT32_MAX; }
+  const uint32_t peers = __match_any_sync(0xffffffffu, c1 ? owner : 32u + lane);
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  const int rounds = __reduce_max_sync(0xffffffffu, c1 ? __popc(peers) : 0);
+  for (int r = 0; r < rounds; ++r) {
+    if (c1 && rank == r) sts_v4(qa + kQMail + owner * 16, v1, i1, v2, i2);
+    __syncwarp();
+    const int4 mb = lds_v4(qa + kQMail + lane * 16);
+    sts_v4(qa + kQMail + lane * 16, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
+    insert_vi(s, mb.x, mb.y);
+    insert_vi(s, mb.z, mb.w);
+    __syncwarp();
+  }
+  if (lane == 0) sts_32(qa + kQCount, 0);
+  __syncwarp();
+  update_thr(s, nt_min);
+}
+
+// Filtered update with one 32-column chunk; qn = events queued so far (warp-uniform).
+__device__ __forceinline__ void chunk_filtered(const uint32_t (&r)[32], uint32_t qa, int& qn,
+                                               int lane, const int32_t* __restrict__ ckey,
+                                               int crow, int cidx, int t_row0, int nt_min,
+                                               RowTop2& s) {
+  const uint32_t meta0 = static_cast<uint32_t>(crow) | (static_cast<uint32_t>(lane) << kRowBits);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
+    const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
+    const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+    if (gm > s.thr) {
+      const int slot = atoms_add(qa + kQCount, 1);
+      if (slot < kQueueSlots) {
+        sts_v4(qa + kQAcc + slot * 32, r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]);
+        sts_v4(qa + kQAcc + slot * 32 + 16, r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
+               r[8 * j + 7]);
+        sts_32(qa + kQMeta + slot * 4, meta0 + 8 * j);
+      }
+    }
+  }
+  __syncwarp();
+  const int n = lds_32(qa + kQCount);
+  if (n > kQueueSlots) {
+    // the chunk does not fit: drop its events again and take the unfiltered path
+    __syncwarp();
+    if (lane == 0) sts_32(qa + kQCount, qn);
+    __syncwarp();
+    chunk_exact(r, ckey, crow, cidx, s);
+    update_thr(s, nt_min);
+  } else {
+    qn = n;
+    if (qn >= kFlushAt) {
+      queue_flush(qa, qn, lane, ckey, t_row0, nt_min, s);
+      qn = 0;
+    }
   }
 }
 
@@ -166,7 +269,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
 
   const uint32_t sA = smem_base + kOffA;
   const uint32_t sB = smem_base + kOffB;
-  const uint32_t sCk = smem_base + kOffCk;
   const uint32_t bar0 = smem_base + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
@@ -200,6 +302,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       }
     fence_mbar_init();
   }
+  if (warp >= kFirstEpiWarp) {
+    const uint32_t qa0 = smem_base + kOffQueue + (warp - kFirstEpiWarp) * kQBytes;
+    sts_v4(qa0 + kQMail + lane * 16, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
+    if (lane == 0) sts_32(qa0 + kQCount, 0);
+  }
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -208,19 +315,18 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // 768 threads leave 80 registers per thread; the control warpgroups (0: producer + idle
-  // warps, 1: MMA issuers) hand their share to the epilogue warpgroups (setmaxnreg, issued at
-  // the top of each role branch so that ptxas allocates per branch)
 
   // Producer and MMA warps run their loops with all 32 lanes and pick the issuing lane with
   // elect.sync: ptxas then keeps descriptors / barrier addresses in uniform registers instead
   // of wrapping every UTCIMMA / UTMALDG in a per-thread waterfall loop (measured: 80 cycles
-  // per MMA with `if (lane == 0)`).
-  if (warp < kFirstMmaWarp) {
-    // ===================================================== TMA producer (warp 0; 1..3 idle)
+  // per MMA with `if (lane == 0)`).  768 threads leave 80 registers per thread; the control
+  // warpgroups hand part of their share to the epilogue warpgroups (setmaxnreg at the top of
+  // each role branch, so that ptxas allocates per branch).
+  if (warp < kFirstEpiWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
     if (warp == 0) {
-      uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0, tile_seq = 0;
+      // ===================================================== TMA producer
+      uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
       int item = blockIdx.x;
       int2 it = item < n_items ? __ldg(items + item) : make_int2(0, 0);
       PairDesc pd = pairs[it.x];
@@ -233,6 +339,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           info[abuf].ntiles = ntiles;
           info[abuf].rows_valid = pd.nq - mblk * kTileM;
           info[abuf].norm_row = pd.q_row0 + mblk * kTileM;
+          info[abuf].t_row0 = pd.t_row0;
+          info[abuf].nt_min = pd.nt_min;
           info[abuf].knn_row = pd.knn_off + static_cast<int64_t>(mblk) * kTileM;
           mbar_arrive_expect_tx(bar_a_full(abuf), kABytes);
           tma_load_2d(sA + abuf * kABytes, &tmap, bar_a_full(abuf), 0, pd.q_row0 + mblk * kTileM);
@@ -255,61 +363,57 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             if (dbg & 1) {                       // timing experiment: no operand traffic
               mbar_arrive(bar_full(stage));
             } else {
-              mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes);
+              mbar_arrive_expect_tx(bar_full(stage), kBBytes);
               tma_load_2d(sB + stage * kBBytes, &tmap, bar_full(stage), 0, row);
-              bulk_load_1d(sCk + (tile_seq % kCkSlots) * kCkBytes, ckey + row, kCkBytes,
-                           bar_full(stage));
             }
           }
           __syncwarp();
-          ++tile_seq;
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
-    }
-  } else if (warp >= kFirstMmaWarp && warp < kFirstEpiWarp) {
-    // ===================================================== MMA issuers: (half mh, parity mp)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
-    const int mh = (warp - kFirstMmaWarp) & 1, mp = (warp - kFirstMmaWarp) >> 1;
-    constexpr uint32_t idesc = make_idesc_u8(kHalfM, kTileN);
-    const uint32_t d_tmem = tmem_base + mp * (2 * kTileN) + mh * kTileN;
-    uint32_t seq = 0, abuf = 0, aphase = 0;     // seq = tiles of this CTA so far
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      mbar_wait(bar_a_full(abuf), aphase);
-      const int ntiles = info[abuf].ntiles;
-      const uint64_t a_desc = make_smem_desc_sw128(sA + abuf * kABytes + mh * kAHalfBytes);
-      bool own_any = false;
-      for (int t = 0; t < ntiles; ++t, ++seq) {
-        if ((seq & 1) != static_cast<uint32_t>(mp)) continue;
-        own_any = true;
-        const uint32_t stage = seq % kStages, phase = (seq / kStages) & 1;
-        mbar_wait(bar_full(stage), phase);
-        if (!(dbg & 2)) mbar_wait(bar_t_empty(mp, mh), ((seq >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t b_desc = make_smem_desc_sw128(sB + stage * kBBytes);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kDim / 32; ++k) {
-            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4)
-            umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
-          }
-          umma_commit(bar_t_full(mp, mh));
-          umma_commit(bar_empty(stage));
-          if (t + 2 >= ntiles) umma_commit(bar_a_empty(abuf));   // this warp's last tile
+    } else if (warp >= kFirstMmaWarp) {
+      // ===================================================== MMA issuers: (half mh, parity mp)
+      const uint32_t mh = (warp - kFirstMmaWarp) & 1, mp = (warp - kFirstMmaWarp) >> 1;
+      constexpr uint32_t idesc = make_idesc_u8(kHalfM, kTileN);
+      const uint32_t d_tmem = tmem_base + mp * (2 * kTileN) + mh * kTileN;
+      uint32_t seq = 0, abuf = 0, aphase = 0;     // seq = tiles of this CTA so far
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(bar_a_full(abuf), aphase);
+        const uint32_t ntiles = info[abuf].ntiles;
+        const uint64_t a_desc = make_smem_desc_sw128(sA + abuf * kABytes + mh * kAHalfBytes);
+        const uint32_t end = seq + ntiles;
+        uint32_t ts = seq + ((seq & 1) != mp);     // first tile of this warp's parity
+        if (ts >= end) {                           // single-tile item of the other parity
+          if (elect_one()) mbar_arrive(bar_a_empty(abuf));
+          __syncwarp();
         }
-        __syncwarp();
+        for (; ts < end; ts += 2) {
+          const uint32_t stage = ts % kStages;
+          mbar_wait(bar_full(stage), (ts / kStages) & 1);
+          if (!(dbg & 2)) mbar_wait(bar_t_empty(mp, mh), ((ts >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t b_desc = make_smem_desc_sw128(sB + stage * kBBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kDim / 32; ++k) {
+              // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in (addr >> 4)
+              umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+            }
+            umma_commit(bar_t_full(mp, mh));
+            umma_commit(bar_empty(stage));
+            if (ts + 2 >= end) umma_commit(bar_a_empty(abuf));   // this warp's last tile
+          }
+          __syncwarp();
+        }
+        seq = end;
+        abuf ^= 1;
+        if (abuf == 0) aphase ^= 1;
       }
-      if (!own_any) {                            // single-tile item of the other parity
-        if (elect_one()) mbar_arrive(bar_a_empty(abuf));
-        __syncwarp();
-      }
-      abuf ^= 1;
-      if (abuf == 0) aphase ^= 1;
     }
-  } else if (warp >= kFirstEpiWarp) {
+  } else {
     // ===================================================== epilogue: running top-2 per row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     const int e = warp - kFirstEpiWarp;            // 4 consecutive warps cover the 4 quarters
@@ -319,16 +423,15 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     const int row_in_blk = half * kHalfM + quarter * 32 + lane;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                             half * kTileN + chalf * kColsPerThread;
-    int4* merge_buf = reinterpret_cast<int4*>(smem_gen + kOffMerge);
+    const uint32_t qa = smem_base + kOffQueue + e * kQBytes;
+    const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
-    uint32_t buf = 0, bphase = 0, tile_seq = 0, abuf = 0, mslot = 0;
+    uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
-      int g1v = INT32_MAX, g2v = INT32_MAX, g1i = INT32_MAX, g2i = INT32_MAX;
-      int ntiles = 1, rows_valid = 0, norm_row = 0;
+      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, -1};
+      int ntiles = 1, rows_valid = 0, norm_row = 0, t_row0 = 0, nt_min = 0;
       int64_t knn_row = 0;
-      // window-local top-2 as packed keys; a window is a pair of train tiles (256 columns,
-      // the 8 column bits of a key); thr = bound on keys that can still enter the top-2
-      int m1 = INT32_MAX, m2 = INT32_MAX, thr = INT32_MAX;
+      int qn = 0;                                   // events in the warp queue (warp-uniform)
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(bar_t_full(buf, half), bphase);
         tc_fence_after();
@@ -336,105 +439,82 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           ntiles = info[abuf].ntiles;
           rows_valid = info[abuf].rows_valid;
           norm_row = info[abuf].norm_row;
+          t_row0 = info[abuf].t_row0;
+          nt_min = info[abuf].nt_min;
           knn_row = info[abuf].knn_row;
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_empty(abuf));
           abuf ^= 1;
         }
-        const int4* ck4 = reinterpret_cast<const int4*>(smem_gen + kOffCk +
-                                                        (tile_seq % kCkSlots) * kCkBytes) +
-                          chalf * (kColsPerThread / 4);
         const uint32_t ta = t_addr + buf * (2 * kTileN);
         if constexpr (kMode >= 2) {
-          // timing experiments only (results are garbage): 2 = drain TMEM, 3 = handshake only
-          if constexpr (kMode == 4) {
-            // fast path of a raw-accumulator filter: 3-input max tree per 8 columns + compare
-            uint32_t r[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld_x32(ta + 32 * c, r);
-              tmem_ld_wait();
-              int gm[4];
+          // timing experiments only (results are garbage):
+          // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
+          if constexpr (kMode == 2 || kMode == 4) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_x32(ta, r0);
+            tmem_ld_x32(ta + 32, r1);
+            tmem_ld_wait();
+            st.g1v = min(st.g1v, static_cast<int>(r0[0] ^ r1[31]));
+            if constexpr (kMode == 4) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-                const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-                gm[j] = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+                const int a = __vimax3_s32(r0[8 * j + 0], r0[8 * j + 1], r0[8 * j + 2]);
+                const int b = __vimax3_s32(r0[8 * j + 3], r0[8 * j + 4], r0[8 * j + 5]);
+                const int c = __vimax3_s32(r1[8 * j + 0], r1[8 * j + 1], r1[8 * j + 2]);
+                const int d = __vimax3_s32(r1[8 * j + 3], r1[8 * j + 4], r1[8 * j + 5]);
+                const int g0 = max(__vimax3_s32(a, b, r0[8 * j + 6]), static_cast<int>(r0[8 * j + 7]));
+                const int g1 = max(__vimax3_s32(c, d, r1[8 * j + 6]), static_cast<int>(r1[8 * j + 7]));
+                if (g0 > st.thr) { st.g1i = g0; ++st.g2v; }
+                if (g1 > st.thr) { st.g1i = g1; ++st.g2i; }
               }
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (gm[j] > thr) { m1 = gm[j]; ++m2; }       // stands in for a predicated append
             }
-          }
-          if constexpr (kMode == 2) {
-            uint32_t r[32];
-            tmem_ld_x32(ta, r);
-            tmem_ld_wait();
-            m1 = min(m1, static_cast<int>(r[0] ^ r[31]));
-            tmem_ld_x32(ta + 32, r);
-            tmem_ld_wait();
-            m2 = min(m2, static_cast<int>(r[0] ^ r[31]));
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
         } else {
-          uint32_t r[32];
-          int k[32];
-          tmem_ld_x32(ta, r);
-          tmem_ld_wait();
-          make_keys(r, ck4, k);
-          tmem_ld_x32(ta + 32, r);          // in flight while the first chunk is filtered
-          chunk_top2<kMode>(k, m1, m2, thr);
+          // pull this thread's 64 accumulators out of TMEM and hand the buffer back at once
+          uint32_t r0[32], r1[32];
+          tmem_ld_x32(ta, r0);
+          tmem_ld_x32(ta + 32, r1);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));   // TMEM reads of this tile done
-          make_keys(r, ck4 + 8, k);
-          chunk_top2<kMode>(k, m1, m2, thr);
-        }
-        if ((t & 1) || t == ntiles - 1) {
-          // merge the window's top-2 into the running (value, index) pairs; later windows
-          // hold larger indices, so strict '<' keeps the lower index on equal distance.
-          const int base = (t & ~1) * kTileN;
-          const int v1 = m1 >> (kKeyShift + 1), i1 = base + (m1 & (2 * kTileN - 1));
-          const int v2 = m2 >> (kKeyShift + 1), i2 = base + (m2 & (2 * kTileN - 1));
-          if (v1 < g1v) {
-            g2v = g1v; g2i = g1i;
-            g1v = v1;  g1i = i1;
-          } else if (v1 < g2v) {
-            g2v = v1;  g2i = i1;
+          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
+          const int cidx = t * kTileN + chalf * kColsPerThread;   // train index of column 0
+          const int crow = t_row0 + cidx;                         // its bank row
+          if (kMode == 0 || t < kExactTiles) {
+            chunk_exact(r0, ckey, crow, cidx, st);
+            chunk_exact(r1, ckey, crow + 32, cidx + 32, st);
+            update_thr(st, nt_min);
+          } else {
+            chunk_filtered(r0, qa, qn, lane, ckey, crow, cidx, t_row0, nt_min, st);
+            chunk_filtered(r1, qa, qn, lane, ckey, crow + 32, cidx + 32, t_row0, nt_min, st);
           }
-          if (v2 < g2v) {
-            g2v = v2;  g2i = i2;
-          }
-          m1 = INT32_MAX;
-          m2 = INT32_MAX;
-          // key < (g2v << 8)  <=>  value < g2v
-          thr = g2v < (1 << 22) ? g2v << (kKeyShift + 1) : INT32_MAX;
         }
-        ++tile_seq;
         if (++buf == kAccBufs) {
           buf = 0;
           bphase ^= 1;
         }
       }
+      if (kMode == 1 && qn > 0) queue_flush(qa, qn, lane, ckey, t_row0, nt_min, st);
       // merge the two column halves of the row: the upper half hands its top-2 over
-      int4* slot = merge_buf + mslot * kTileM + row_in_blk;
+      const uint32_t slot = merge_addr + mslot * (kTileM * 16);
       mslot ^= 1;
-      if (chalf == 1) *slot = make_int4(g1v, g1i, g2v, g2i);
+      if (chalf == 1) sts_v4(slot, st.g1v, st.g1i, st.g2v, st.g2i);
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       if (chalf == 0) {
-        const int4 o = *slot;
-        insert_vi(o.x, o.y, g1v, g1i, g2v, g2i);
-        insert_vi(o.z, o.w, g1v, g1i, g2v, g2i);
+        const int4 o = lds_v4(slot);
+        insert_vi(st, o.x, o.y);
+        insert_vi(st, o.z, o.w);
         if (row_in_blk < rows_valid) {
           const int nq2 = __ldg(norm + norm_row + row_in_blk);
           Knn2 out;
-          out.j0 = g1i;
-          out.j1 = g2i;
-          out.d0 = g1v + nq2;
-          out.d1 = g2v + nq2;
+          out.j0 = st.g1i;
+          out.j1 = st.g2i;
+          out.d0 = st.g1v + nq2;
+          out.d1 = st.g2v + nq2;
           *reinterpret_cast<int4*>(&knn_out[knn_row + row_in_blk]) =
               *reinterpret_cast<int4*>(&out);
         }

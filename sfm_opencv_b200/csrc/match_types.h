@@ -17,6 +17,8 @@ struct PairDesc {
   int32_t t_row0;    // first bank row of the train image
   int32_t nq;        // query descriptors
   int32_t nt;        // train descriptors
+  int32_t nt_min;    // min |t|^2 over the train image (bound used by the epilogue filter)
+  int32_t pad;
   int64_t knn_off;   // first row of this pair in the kNN result array
 };
 

@@ -6,7 +6,7 @@ from oracle import synth
 bank = synth.image_bank(16, 8192)
 pairs = [(i, j) for i in range(16) for j in range(i + 1, 16)]
 out = {}
-for mode in (1, 2, 3, 4):
+for mode in (1, 0, 3, 4):
     os.environ["SFM_KNN_MODE"] = str(mode)
     with sfm.Context(0) as c:
         c.upload_descriptors(bank)
