@@ -25,15 +25,13 @@
 // op per accumulator (tools/ubench.cu): the fast path looks only at RAW dot products.
 // A column j can enter a row's top-2 only if |t_j|^2 - 2 q.t_j < v2 (v2 = second-best value so
 // far), hence only if q.t_j > (min_j |t_j|^2 - v2) / 2 =: thr.  Per group of 8 columns: a
-// 3-input-max tree (0.5 op/element) and one compare against the row's thr.  Groups that pass
-// (~2 ln(n) per row and sweep) are appended -- raw accumulators + (bank row, owner lane) -- to
-// a per-warp queue in shared memory.  The queue is drained cooperatively: lane L rebuilds
-// the exact packed keys of event L from the column keys in global memory, takes their top-2
-// and mails it to the owner lane, which merges it into its running (value, index) pairs with
-// a lexicographic insert, then tightens thr.  The first two tiles of a sweep and any chunk
-// that would overflow the queue take the unfiltered exact path.  Skipped columns provably
-// have two predecessors that beat them, so results are identical to the unfiltered epilogue
-// (SFM_KNN_MODE=0); a GPU test compares the two bit for bit.
+// 3-input-max tree (0.5 op/element) and one warp vote against the rows' thr.  Only groups in
+// which some row of the warp passes get their exact packed keys built (8 IMADs with the
+// column keys staged in shared memory) and inserted (20 min/max); that is harmless for the
+// rows that did not pass.  Skipped columns provably have two predecessors that beat them,
+// so results are identical to the unfiltered epilogue (SFM_KNN_MODE=0); a GPU test compares
+// the two bit for bit.  The two threads that share a row (column halves) exchange their
+// second-best value through shared memory once per 256-column window to tighten thr.
 // The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -57,14 +55,12 @@ constexpr int kRegsEpi = 96;                    // setmaxnreg: epilogue warpgrou
 static_assert(8 * kRegsCtl + 16 * kRegsEpi <= 24 * 80, "register pool of the CTA (768 x 80)");
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
-constexpr int kExactTiles = 2;                  // tiles at the start of a sweep done unfiltered
-constexpr int kQueueSlots = 32;                 // events per warp queue (one per lane to drain)
-constexpr int kFlushAt = 20;                    // drain when this many events are queued
-constexpr int kRowBits = 26;                    // bank rows < 2^26 (event meta = row | lane << 26)
+constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
 
 constexpr uint32_t kABytes = kTileM * kDim;     // 32 KB
 constexpr uint32_t kAHalfBytes = kHalfM * kDim; // 16 KB
 constexpr uint32_t kBBytes = kTileN * kDim;     // 16 KB
+constexpr uint32_t kCkBytes = kTileN * 4;       // 512 B
 
 // What the producer tells the MMA and epilogue warps about an item.
 struct ItemInfo {
@@ -77,25 +73,19 @@ struct ItemInfo {
   int64_t knn_row;      // first output row of the block
 };
 
-// per epilogue warp: event queue + mailboxes (byte offsets inside the warp's block)
-constexpr uint32_t kQAcc = 0;                              // [32 slots][8] raw accumulators
-constexpr uint32_t kQMeta = kQAcc + kQueueSlots * 32;      // [32] bank row | owner lane << 26
-constexpr uint32_t kQMail = kQMeta + kQueueSlots * 4;      // [32 lanes] (v1, i1, v2, i2)
-constexpr uint32_t kQCount = kQMail + 32 * 16;             // events queued
-constexpr uint32_t kQBytes = kQCount + 16;
-
 // dynamic shared memory map (offsets from a 1024-byte aligned base)
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + 2 * kABytes;
-constexpr uint32_t kOffInfo = kOffB + kStages * kBBytes;
+constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
+constexpr uint32_t kOffInfo = kOffCk + kCkSlots * kCkBytes;
 constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
-constexpr uint32_t kOffQueue = kOffMerge + 2 * kTileM * 16;
-constexpr uint32_t kOffBar = kOffQueue + kEpiWarps * kQBytes;
+constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int2
+constexpr uint32_t kOffBar = kOffShare + kTileM * 16;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kKnnSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
 static_assert(kKnnSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(ItemInfo) == 32 && kQBytes % 16 == 0, "smem layout");
+static_assert(sizeof(ItemInfo) == 32, "smem layout");
 
 // (a1 <= a2), (b1 <= b2) -> the two smallest of the four, sorted.
 __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
@@ -124,23 +114,11 @@ __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
   merge_top2(m1, m2, lo[0], hi[0]);
 }
 
-// top-2 (as packed keys) of the 8 columns starting at bank row `row`, accumulators a[0..7]
-__device__ __forceinline__ void group_top2(const uint32_t* a, const int32_t* __restrict__ ckey,
-                                           int row, int& e1, int& e2) {
-  const int4 c0 = __ldg(reinterpret_cast<const int4*>(ckey + row));
-  const int4 c1 = __ldg(reinterpret_cast<const int4*>(ckey + row) + 1);
-  int k[8];
-  k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
-  k[2] = make_key(a[2], c0.z); k[3] = make_key(a[3], c0.w);
-  k[4] = make_key(a[4], c1.x); k[5] = make_key(a[5], c1.y);
-  k[6] = make_key(a[6], c1.z); k[7] = make_key(a[7], c1.w);
-  insert8(k, e1, e2);
-}
-
 // Running state of one epilogue thread (one query row, half of the columns).
 struct RowTop2 {
-  int g1v, g1i, g2v, g2i;   // best / second best: value = |t|^2 - 2 q.t, index in the train image
-  int thr;                  // q.t must exceed this to matter: (nt_min - g2v) >> 1
+  int g1v, g1i, g2v, g2i;   // best / second best of the finished windows: value = |t|^2 - 2 q.t
+  int m1, m2;               // top-2 of the current 256-column window as packed keys
+  int thr;                  // q.t must exceed this to matter: (nt_min - second best) >> 1
 };
 
 __device__ __forceinline__ bool lex_lt(int v, int i, int gv, int gi) {
@@ -158,102 +136,47 @@ __device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
   s.g1i = b1 ? i : s.g1i;
 }
 
-__device__ __forceinline__ void update_thr(RowTop2& s, int nt_min) {
-  s.thr = s.g2v < (1 << 22) ? (nt_min - s.g2v) >> 1 : -1;
+// exact keys of the 8 columns of group j (column keys from the shared-memory ring) -> (m1, m2)
+__device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr, RowTop2& s) {
+  const int4 c0 = lds_v4(ck_addr), c1 = lds_v4(ck_addr + 16);
+  int k[8];
+  k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
+  k[2] = make_key(a[2], c0.z); k[3] = make_key(a[3], c0.w);
+  k[4] = make_key(a[4], c1.x); k[5] = make_key(a[5], c1.y);
+  k[6] = make_key(a[6], c1.z); k[7] = make_key(a[7], c1.w);
+  insert8(k, s.m1, s.m2);
 }
 
-// Unfiltered exact update with the 32 columns of one chunk (bank rows crow.., indices cidx..).
-__device__ __forceinline__ void chunk_exact(const uint32_t (&r)[32],
-                                            const int32_t* __restrict__ ckey, int crow, int cidx,
-                                            RowTop2& s) {
-  int e1 = INT32_MAX, e2 = INT32_MAX;
+// Top-2 update with the 32 columns of one chunk; ck_addr = shared address of their keys.
+//   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
+//   kMode 1: only groups whose raw maximum beats the bound of some row of the warp.
+template <int kMode>
+__device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
+                                             int nt_min, RowTop2& s) {
+  if constexpr (kMode == 0) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) group_top2(&r[8 * g], ckey, crow + 8 * g, e1, e2);
-  const int base = cidx & ~(2 * kTileN - 1);     // packed keys carry 8 column bits
-  insert_vi(s, e1 >> (kKeyShift + 1), base + (e1 & (2 * kTileN - 1)));
-  insert_vi(s, e2 >> (kKeyShift + 1), base + (e2 & (2 * kTileN - 1)));
-}
-
-// Cooperative drain of the warp queue at shared address qa (n events, n <= 32): lane L
-// rebuilds the exact keys of event L, drops what can no longer enter the owner's top-2 and
-// mails the rest to the owner lane, one event per owner and round.
-__device__ __forceinline__ void queue_flush(uint32_t qa, int n, int lane,
-                                            const int32_t* __restrict__ ckey, int t_row0,
-                                            int nt_min, RowTop2& s) {
-  int v1 = INT32_MAX, i1 = INT32_MAX, v2 = INT32_MAX, i2 = INT32_MAX;
-  uint32_t owner = lane;
-  if (lane < n) {
-    const uint32_t meta = static_cast<uint32_t>(lds_32(qa + kQMeta + lane * 4));
-    const int row = static_cast<int>(meta & ((1u << kRowBits) - 1));
-    owner = meta >> kRowBits;
-    const int4 a0 = lds_v4(qa + kQAcc + lane * 32), a1 = lds_v4(qa + kQAcc + lane * 32 + 16);
-    const uint32_t a[8] = {static_cast<uint32_t>(a0.x), static_cast<uint32_t>(a0.y),
-                           static_cast<uint32_t>(a0.z), static_cast<uint32_t>(a0.w),
-                           static_cast<uint32_t>(a1.x), static_cast<uint32_t>(a1.y),
-                           static_cast<uint32_t>(a1.z), static_cast<uint32_t>(a1.w)};
-    int e1 = INT32_MAX, e2 = INT32_MAX;
-    group_top2(a, ckey, row, e1, e2);
-    const int base = (row - t_row0) & ~(2 * kTileN - 1);
-    v1 = e1 >> (kKeyShift + 1); i1 = base + (e1 & (2 * kTileN - 1));
-    v2 = e2 >> (kKeyShift + 1); i2 = base + (e2 & (2 * kTileN - 1));
-  }
-  // the owner's current second best: anything not below it cannot enter any more
-  const int ov = __shfl_sync(0xffffffffu, s.g2v, owner);
-  const int oi = __shfl_sync(0xffffffffu, s.g2i, owner);
-  const bool c1 = lex_lt(v1, i1, ov, oi);          // false for lanes without an event
-  if (!lex_lt(v2, i2, ov, oi)) { v2 = INT32_MAX; i2 = INT32_MAX; }
-  const uint32_t peers = __match_any_sync(0xffffffffu, c1 ? owner : 32u + lane);
-  const int rank = __popc(peers & ((1u << lane) - 1u));
-  const int rounds = __reduce_max_sync(0xffffffffu, c1 ? __popc(peers) : 0);
-  for (int r = 0; r < rounds; ++r) {
-    if (c1 && rank == r) sts_v4(qa + kQMail + owner * 16, v1, i1, v2, i2);
-    __syncwarp();
-    const int4 mb = lds_v4(qa + kQMail + lane * 16);
-    sts_v4(qa + kQMail + lane * 16, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
-    insert_vi(s, mb.x, mb.y);
-    insert_vi(s, mb.z, mb.w);
-    __syncwarp();
-  }
-  if (lane == 0) sts_32(qa + kQCount, 0);
-  __syncwarp();
-  update_thr(s, nt_min);
-}
-
-// Filtered update with one 32-column chunk; qn = events queued so far (warp-uniform).
-__device__ __forceinline__ void chunk_filtered(const uint32_t (&r)[32], uint32_t qa, int& qn,
-                                               int lane, const int32_t* __restrict__ ckey,
-                                               int crow, int cidx, int t_row0, int nt_min,
-                                               RowTop2& s) {
-  const uint32_t meta0 = static_cast<uint32_t>(crow) | (static_cast<uint32_t>(lane) << kRowBits);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-    const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-    const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
-    if (gm > s.thr) {
-      const int slot = atoms_add(qa + kQCount, 1);
-      if (slot < kQueueSlots) {
-        sts_v4(qa + kQAcc + slot * 32, r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]);
-        sts_v4(qa + kQAcc + slot * 32 + 16, r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
-               r[8 * j + 7]);
-        sts_32(qa + kQMeta + slot * 4, meta0 + 8 * j);
-      }
-    }
-  }
-  __syncwarp();
-  const int n = lds_32(qa + kQCount);
-  if (n > kQueueSlots) {
-    // the chunk does not fit: drop its events again and take the unfiltered path
-    __syncwarp();
-    if (lane == 0) sts_32(qa + kQCount, qn);
-    __syncwarp();
-    chunk_exact(r, ckey, crow, cidx, s);
-    update_thr(s, nt_min);
+    for (int j = 0; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
   } else {
-    qn = n;
-    if (qn >= kFlushAt) {
-      queue_flush(qa, qn, lane, ckey, t_row0, nt_min, s);
-      qn = 0;
+    int gm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
+      const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
+      gm[j] = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+    }
+    // the four votes are independent (thr is tightened afterwards)
+    const bool h0 = __any_sync(0xffffffffu, gm[0] > s.thr);
+    const bool h1 = __any_sync(0xffffffffu, gm[1] > s.thr);
+    const bool h2 = __any_sync(0xffffffffu, gm[2] > s.thr);
+    const bool h3 = __any_sync(0xffffffffu, gm[3] > s.thr);
+    if (h0) group_insert(&r[0], ck_addr, s);
+    if (h1) group_insert(&r[8], ck_addr + 32, s);
+    if (h2) group_insert(&r[16], ck_addr + 64, s);
+    if (h3) group_insert(&r[24], ck_addr + 96, s);
+    if (h0 | h1 | h2 | h3) {
+      // the window's second best also bounds what can still enter (values, not keys)
+      const int w2 = s.m2 >> (kKeyShift + 1);
+      if (w2 < (1 << 22)) s.thr = max(s.thr, (nt_min - w2) >> 1);
     }
   }
 }
@@ -269,6 +192,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
 
   const uint32_t sA = smem_base + kOffA;
   const uint32_t sB = smem_base + kOffB;
+  const uint32_t sCk = smem_base + kOffCk;
   const uint32_t bar0 = smem_base + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
@@ -302,11 +226,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       }
     fence_mbar_init();
   }
-  if (warp >= kFirstEpiWarp) {
-    const uint32_t qa0 = smem_base + kOffQueue + (warp - kFirstEpiWarp) * kQBytes;
-    sts_v4(qa0 + kQMail + lane * 16, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
-    if (lane == 0) sts_32(qa0 + kQCount, 0);
-  }
+  if (threadIdx.x < kTileM)    // (item tag, second-best value) slots of the row-sharing threads
+    sts_v4(smem_base + kOffShare + threadIdx.x * 16, 0xffffffffu, 0, 0xffffffffu, 0);
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -326,7 +247,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
     if (warp == 0) {
       // ===================================================== TMA producer
-      uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
+      uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0, tile_seq = 0;
       int item = blockIdx.x;
       int2 it = item < n_items ? __ldg(items + item) : make_int2(0, 0);
       PairDesc pd = pairs[it.x];
@@ -363,11 +284,14 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             if (dbg & 1) {                       // timing experiment: no operand traffic
               mbar_arrive(bar_full(stage));
             } else {
-              mbar_arrive_expect_tx(bar_full(stage), kBBytes);
+              mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes);
               tma_load_2d(sB + stage * kBBytes, &tmap, bar_full(stage), 0, row);
+              bulk_load_1d(sCk + (tile_seq % kCkSlots) * kCkBytes, ckey + row, kCkBytes,
+                           bar_full(stage));
             }
           }
           __syncwarp();
+          ++tile_seq;
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -423,15 +347,15 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     const int row_in_blk = half * kHalfM + quarter * 32 + lane;
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                             half * kTileN + chalf * kColsPerThread;
-    const uint32_t qa = smem_base + kOffQueue + e * kQBytes;
     const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
+    const uint32_t share_own = smem_base + kOffShare + row_in_blk * 16 + chalf * 8;
+    const uint32_t share_other = smem_base + kOffShare + row_in_blk * 16 + (chalf ^ 1) * 8;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
-    uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0;
+    uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
-      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, -1};
-      int ntiles = 1, rows_valid = 0, norm_row = 0, t_row0 = 0, nt_min = 0;
+      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, -1};
+      int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0;
       int64_t knn_row = 0;
-      int qn = 0;                                   // events in the warp queue (warp-uniform)
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(bar_t_full(buf, half), bphase);
         tc_fence_after();
@@ -439,7 +363,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           ntiles = info[abuf].ntiles;
           rows_valid = info[abuf].rows_valid;
           norm_row = info[abuf].norm_row;
-          t_row0 = info[abuf].t_row0;
           nt_min = info[abuf].nt_min;
           knn_row = info[abuf].knn_row;
           __syncwarp();
@@ -482,23 +405,32 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-          const int cidx = t * kTileN + chalf * kColsPerThread;   // train index of column 0
-          const int crow = t_row0 + cidx;                         // its bank row
-          if (kMode == 0 || t < kExactTiles) {
-            chunk_exact(r0, ckey, crow, cidx, st);
-            chunk_exact(r1, ckey, crow + 32, cidx + 32, st);
-            update_thr(st, nt_min);
-          } else {
-            chunk_filtered(r0, qa, qn, lane, ckey, crow, cidx, t_row0, nt_min, st);
-            chunk_filtered(r1, qa, qn, lane, ckey, crow + 32, cidx + 32, t_row0, nt_min, st);
+          const uint32_t ck_addr = sCk + (tile_seq % kCkSlots) * kCkBytes + chalf * (kColsPerThread * 4);
+          chunk_update<kMode>(r0, ck_addr, nt_min, st);
+          chunk_update<kMode>(r1, ck_addr + 128, nt_min, st);
+          if ((t & 1) || t == ntiles - 1) {
+            // close the 256-column window: merge its packed top-2 into the (value, index)
+            // pairs, then tighten the bound, also with the row partner's second best
+            const int base = (t & ~1) * kTileN;
+            insert_vi(st, st.m1 >> (kKeyShift + 1), base + (st.m1 & (2 * kTileN - 1)));
+            insert_vi(st, st.m2 >> (kKeyShift + 1), base + (st.m2 & (2 * kTileN - 1)));
+            st.m1 = INT32_MAX;
+            st.m2 = INT32_MAX;
+            int bound = st.g2v;
+            if (kMode == 1) {
+              sts_v2(share_own, item, st.g2v);
+              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
+              if (o.x == item && o.y < (1 << 22)) bound = min(bound, o.y + 1);
+            }
+            st.thr = bound < (1 << 22) ? (nt_min - bound) >> 1 : -1;
           }
         }
+        ++tile_seq;
         if (++buf == kAccBufs) {
           buf = 0;
           bphase ^= 1;
         }
       }
-      if (kMode == 1 && qn > 0) queue_flush(qa, qn, lane, ckey, t_row0, nt_min, st);
       // merge the two column halves of the row: the upper half hands its top-2 over
       const uint32_t slot = merge_addr + mslot * (kTileM * 16);
       mslot ^= 1;
