@@ -76,6 +76,15 @@ __device__ __forceinline__ void sym4_mul(const Sym4& a, double& x0, double& x1, 
   x0 = y0; x1 = y1; x2 = y2; x3 = y3;
 }
 
+// 2^-e for x = m * 2^e (m in [1,2)): exact scaling factor from the exponent bits; 1 for
+// zero / denormal / non-finite input.
+__device__ __forceinline__ double pow2_inv(double x) {
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) & 0x7ff;
+  const int ne = 2046 - e;                       // biased exponent of 2^-(e - 1023)
+  return (e > 0 && e < 2046) ? __hiloint2double(ne << 20, 0) : 1.0;
+}
+
 __global__ void __launch_bounds__(256)
 triangulate_kernel(const float* __restrict__ P, const float* __restrict__ xy, int n_views,
                    int64_t n_pts, float* __restrict__ X4, double* __restrict__ xyz) {
@@ -98,9 +107,10 @@ triangulate_kernel(const float* __restrict__ P, const float* __restrict__ xy, in
       sym4_add_row(m, x * q[8] - q[0], x * q[9] - q[1], x * q[10] - q[2], x * q[11] - q[3]);
       sym4_add_row(m, y * q[8] - q[4], y * q[9] - q[5], y * q[10] - q[6], y * q[11] - q[7]);
     }
-    // scale so that cofactors (cubic in M) stay far from overflow for any pixel scale
+    // scale so that cofactors (cubic in M) stay far from overflow for any pixel scale:
+    // an exact power of two built from the exponent of the trace (no division)
     const double tr = m.m00 + m.m11 + m.m22 + m.m33;
-    const double sc = tr > 0.0 ? 1.0 / tr : 1.0;
+    const double sc = pow2_inv(tr);
     m.m00 *= sc; m.m01 *= sc; m.m02 *= sc; m.m03 *= sc; m.m11 *= sc;
     m.m12 *= sc; m.m13 *= sc; m.m22 *= sc; m.m23 *= sc; m.m33 *= sc;
     const Sym4 adj = sym4_adjugate(m);
@@ -111,13 +121,17 @@ triangulate_kernel(const float* __restrict__ P, const float* __restrict__ xy, in
     if (fabs(adj.m33) > best) { best = fabs(adj.m33); x0 = adj.m03; x1 = adj.m13; x2 = adj.m23; x3 = adj.m33; }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-      const double inv = best > 0.0 ? 1.0 / best : 1.0;
+      const double inv = pow2_inv(best);
       x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
       sym4_mul(adj, x0, x1, x2, x3);
       best = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(x2), fabs(x3)));
     }
-    const double nrm = sqrt(x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3);
-    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    {
+      const double inv = pow2_inv(best);
+      x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
+    }
+    const double n2 = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;   // in [1, 4] after the scaling
+    const double inv = n2 > 0.0 ? rsqrt(n2) : 0.0;
     // cv::triangulatePoints returns the points' dtype: float32 (pts2d are Point2f, :1147)
     const float f0 = static_cast<float>(x0 * inv), f1 = static_cast<float>(x1 * inv);
     const float f2 = static_cast<float>(x2 * inv), f3 = static_cast<float>(x3 * inv);
@@ -176,6 +190,23 @@ __device__ __forceinline__ double huber_rho(double s, double delta) {
   return s <= b ? s : 2.0 * delta * sqrt(s) - b;
 }
 
+__device__ __forceinline__ double2 residual_one(double fx, double fy, double cx, double cy,
+                                                const double* __restrict__ cam,
+                                                const double* __restrict__ pts, int c, int j,
+                                                float2 o) {
+  const double* R = cam + 12 * static_cast<int64_t>(c);
+  const double* Xp = pts + 3 * static_cast<int64_t>(j);
+  const double X = __ldg(Xp), Y = __ldg(Xp + 1), Z = __ldg(Xp + 2);
+  const double p0 = __ldg(R + 0) * X + __ldg(R + 1) * Y + __ldg(R + 2) * Z + __ldg(R + 9);
+  const double p1 = __ldg(R + 3) * X + __ldg(R + 4) * Y + __ldg(R + 5) * Z + __ldg(R + 10);
+  const double p2 = __ldg(R + 6) * X + __ldg(R + 7) * Y + __ldg(R + 8) * Z + __ldg(R + 11);
+  // xp = p0 / p2, yp = p1 / p2 (:166-167); the two quotients are kept as true divisions so
+  // that the result rounds exactly like the reference's double arithmetic
+  const double x = p0 / p2, y = p1 / p2;
+  return make_double2(fx * x + cx - static_cast<double>(o.x),
+                      fy * y + cy - static_cast<double>(o.y));
+}
+
 __global__ void __launch_bounds__(256)
 residual_kernel(double fx, double fy, double cx, double cy, const double* __restrict__ cam,
                 const double* __restrict__ pts, const int32_t* __restrict__ cam_idx,
@@ -183,24 +214,31 @@ residual_kernel(double fx, double fy, double cx, double cy, const double* __rest
                 int64_t n_obs, double huber_delta, double* __restrict__ resid,
                 double* __restrict__ block_cost) {
   double cost = 0.0;
+  // two observations per thread and iteration: 8-byte index loads, one 16-byte observation
+  // load, two 16-byte residual stores in flight
+  const int64_t n2 = n_obs >> 1;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n_obs;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n2;
        k += stride) {
-    const int c = __ldcs(cam_idx + k);
-    const int j = __ldcs(pt_idx + k);
-    const float2 o = __ldcs(reinterpret_cast<const float2*>(obs_xy) + k);
-    const double* R = cam + 12 * static_cast<int64_t>(c);
-    const double X = __ldg(pts + 3 * static_cast<int64_t>(j));
-    const double Y = __ldg(pts + 3 * static_cast<int64_t>(j) + 1);
-    const double Z = __ldg(pts + 3 * static_cast<int64_t>(j) + 2);
-    const double p0 = __ldg(R + 0) * X + __ldg(R + 1) * Y + __ldg(R + 2) * Z + __ldg(R + 9);
-    const double p1 = __ldg(R + 3) * X + __ldg(R + 4) * Y + __ldg(R + 5) * Z + __ldg(R + 10);
-    const double p2 = __ldg(R + 6) * X + __ldg(R + 7) * Y + __ldg(R + 8) * Z + __ldg(R + 11);
-    const double x = p0 / p2, y = p1 / p2;
-    const double r0 = fx * x + cx - static_cast<double>(o.x);
-    const double r1 = fy * y + cy - static_cast<double>(o.y);
-    if (resid != nullptr) __stcs(reinterpret_cast<double2*>(resid) + k, make_double2(r0, r1));
-    if (block_cost != nullptr) cost += huber_rho(r0 * r0 + r1 * r1, huber_delta);
+    const int2 c = __ldcs(reinterpret_cast<const int2*>(cam_idx) + k);
+    const int2 j = __ldcs(reinterpret_cast<const int2*>(pt_idx) + k);
+    const float4 o = __ldcs(reinterpret_cast<const float4*>(obs_xy) + k);
+    const double2 r0 = residual_one(fx, fy, cx, cy, cam, pts, c.x, j.x, make_float2(o.x, o.y));
+    const double2 r1 = residual_one(fx, fy, cx, cy, cam, pts, c.y, j.y, make_float2(o.z, o.w));
+    if (resid != nullptr) {
+      __stcs(reinterpret_cast<double2*>(resid) + 2 * k, r0);
+      __stcs(reinterpret_cast<double2*>(resid) + 2 * k + 1, r1);
+    }
+    if (block_cost != nullptr)
+      cost += huber_rho(r0.x * r0.x + r0.y * r0.y, huber_delta) +
+              huber_rho(r1.x * r1.x + r1.y * r1.y, huber_delta);
+  }
+  if ((n_obs & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t k = n_obs - 1;
+    const float2 o = reinterpret_cast<const float2*>(obs_xy)[k];
+    const double2 r = residual_one(fx, fy, cx, cy, cam, pts, cam_idx[k], pt_idx[k], o);
+    if (resid != nullptr) reinterpret_cast<double2*>(resid)[k] = r;
+    if (block_cost != nullptr) cost += huber_rho(r.x * r.x + r.y * r.y, huber_delta);
   }
   if (block_cost != nullptr) {
     __shared__ double s_part[8];

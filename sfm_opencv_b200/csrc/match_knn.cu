@@ -147,33 +147,38 @@ __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr
   insert8(k, s.m1, s.m2);
 }
 
-// Top-2 update with the 32 columns of one chunk; ck_addr = shared address of their keys.
+// Top-2 update with the thread's 64 columns of one tile (two 32-column chunks);
+// ck_addr = shared address of their keys.
 //   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
-//   kMode 1: only groups whose raw maximum beats the bound of some row of the warp.
+//   kMode 1: only groups whose raw maximum beats the bound of some row of the warp.  All
+//            eight 3-input-max trees and votes are issued before any insert, so they overlap.
 template <int kMode>
-__device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
-                                             int nt_min, RowTop2& s) {
+__device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint32_t (&r1)[32],
+                                            uint32_t ck_addr, int nt_min, RowTop2& s) {
   if constexpr (kMode == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
-  } else {
-    int gm[4];
+    for (int j = 0; j < 4; ++j) group_insert(&r0[8 * j], ck_addr + 32 * j, s);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-      const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-      gm[j] = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+    for (int j = 0; j < 4; ++j) group_insert(&r1[8 * j], ck_addr + 128 + 32 * j, s);
+  } else {
+    bool h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t* r = j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)];
+      const int a = __vimax3_s32(r[0], r[1], r[2]);
+      const int b = __vimax3_s32(r[3], r[4], r[5]);
+      const int gm = max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
+      h[j] = __any_sync(0xffffffffu, gm > s.thr);
     }
-    // the four votes are independent (thr is tightened afterwards)
-    const bool h0 = __any_sync(0xffffffffu, gm[0] > s.thr);
-    const bool h1 = __any_sync(0xffffffffu, gm[1] > s.thr);
-    const bool h2 = __any_sync(0xffffffffu, gm[2] > s.thr);
-    const bool h3 = __any_sync(0xffffffffu, gm[3] > s.thr);
-    if (h0) group_insert(&r[0], ck_addr, s);
-    if (h1) group_insert(&r[8], ck_addr + 32, s);
-    if (h2) group_insert(&r[16], ck_addr + 64, s);
-    if (h3) group_insert(&r[24], ck_addr + 96, s);
-    if (h0 | h1 | h2 | h3) {
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (h[j]) {
+        group_insert(j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)], ck_addr + 32 * j, s);
+        any = true;
+      }
+    }
+    if (any) {
       // the window's second best also bounds what can still enter (values, not keys)
       const int w2 = s.m2 >> (kKeyShift + 1);
       if (w2 < (1 << 22)) s.thr = max(s.thr, (nt_min - w2) >> 1);
@@ -406,8 +411,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
           const uint32_t ck_addr = sCk + (tile_seq % kCkSlots) * kCkBytes + chalf * (kColsPerThread * 4);
-          chunk_update<kMode>(r0, ck_addr, nt_min, st);
-          chunk_update<kMode>(r1, ck_addr + 128, nt_min, st);
+          tile_update<kMode>(r0, r1, ck_addr, nt_min, st);
           if ((t & 1) || t == ntiles - 1) {
             // close the 256-column window: merge its packed top-2 into the (value, index)
             // pairs, then tighten the bound, also with the row partner's second best

@@ -131,3 +131,24 @@ def test_residual_errors(ctx):
         ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], [0, 1], [0, 10], np.zeros((2, 2)))
     r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], [], [], np.zeros((0, 2)))
     assert r.shape == (0, 2) and cost == 0.0
+
+
+def test_config5_size_properties(ctx):
+    """BASELINE config 5 size (4M points): size-independent properties instead of the oracle:
+    unit-norm homogeneous columns, noiseless round trip (triangulate the exact projections ->
+    reproject -> zero residual), and linearity of the residual in the observation."""
+    n = 4_000_000
+    sc = synth.scene(n, 2, seed=11, noise_px=0.0)
+    X4, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+    nrm = np.sqrt((X4.astype(np.float64) ** 2).sum(0))
+    assert np.abs(nrm - 1.0).max() < 1e-6
+    rel = G.point_rel_err(xyz, sc["X"])
+    assert np.percentile(rel, 99.9) < 2e-4          # float32 projections limit the recovery
+    cam, pt = synth.observations_camera_major(n, 2)
+    obs = sc["xy"].reshape(-1, 2)
+    r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    assert np.abs(r).max() < 5e-3                    # observations are float32-rounded pixels
+    r2, _ = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs + np.float32(1.0))
+    shifted = (obs + np.float32(1.0)).astype(np.float64) - obs.astype(np.float64)
+    assert np.abs((r - r2) - shifted).max() < 1e-9
+    assert abs(cost - 0.5 * float((r ** 2).sum())) <= 1e-9 * max(1.0, cost)

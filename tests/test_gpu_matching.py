@@ -213,3 +213,44 @@ def test_filtered_epilogue_equals_unfiltered(ctx, monkeypatch):
     for a, b in zip(m0, m1):
         assert np.array_equal(a, b)
     assert np.array_equal(_bits(md0), _bits(md1))
+
+
+def test_stress_pair_65536_train_rows(ctx):
+    """BASELINE config 4 shape on the train axis (65,536 rows = 512 tiles per sweep): full
+    oracle parity on a query subset, plus the self-match property on the whole image."""
+    t = synth.sift_like(65536, 1001)
+    q = synth.sift_like(300, 1000)
+    q[:40] = t[np.arange(40) * 1601 + 7]             # exact copies spread over the sweep
+    t[60000] = t[123]                                # duplicate rows far apart: lower index first
+    _run(ctx, [q, t], [(0, 1)])
+    ctx.upload_descriptors([t])
+    _, _, knn = ctx.match_pairs([(0, 0)], want_knn=True)
+    assert (knn[0]["distance0"] == 0).all()
+    assert (knn[0]["trainIdx0"] <= np.arange(65536)).all()
+    assert knn[0]["trainIdx0"][60000] == 123 and knn[0]["trainIdx1"][123] == 60000
+
+
+def test_sharded_contexts_equal_single(ctx):
+    """The multi-GPU path: contiguous pair blocks (shard_pairs) matched by independent contexts
+    and concatenated in rank order must equal the single-context result bit for bit."""
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200.sharding import shard_pairs
+    sizes = [900, 300, 1500, 700, 2100]
+    bank = [synth.sift_like(n, 300 + i) for i, n in enumerate(sizes)]
+    for j in range(1, len(bank)):
+        bank[j][:200] = bank[j - 1][100:300]
+    pairs = M.all_pairs(len(bank))
+    ctx.upload_descriptors(bank)
+    single, md_single, _ = ctx.match_pairs(pairs)
+    for world in (2, 3):
+        got, md = [], []
+        for lo, hi in shard_pairs(pairs, sizes, world):
+            with sfm.Context(0) as c:
+                c.upload_descriptors(bank)
+                m, d, _ = c.match_pairs(pairs[lo:hi])
+                got += m
+                md += list(d)
+        assert len(got) == len(single)
+        for a, b in zip(got, single):
+            assert np.array_equal(a, b)
+        assert np.array_equal(_bits(np.array(md, np.float32)), _bits(md_single))
