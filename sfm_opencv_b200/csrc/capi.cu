@@ -16,13 +16,13 @@
 namespace sfm {
 // match_knn.cu
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
-                        const int32_t* norm, const PairDesc* pairs, const int2* items,
+                        const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 // match_finalize.cu
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
-                             int32_t* norm, int32_t* ckey, uint32_t* flags, int32_t* min_norm,
-                             cudaStream_t s);
+                             int32_t* norm, int32_t* ckey, int32_t* gmin8, uint32_t* flags,
+                             int32_t* min_norm, cudaStream_t s);
 cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
                           float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
                           int64_t* offsets, cudaStream_t s);
@@ -88,7 +88,7 @@ struct sfm_ctx {
   EncodeTiledFn encode = nullptr;
 
   // descriptor bank (padded rows)
-  DevBuf desc, norm, ckey, flags, stage, img_min;   // img_min: min |row|^2 per image
+  DevBuf desc, norm, ckey, gmin8, flags, stage, img_min;   // img_min: min |row|^2 per image
   std::vector<int32_t> img_min_norm;
   std::vector<int32_t> img_n, img_row0;
   std::vector<int2> h_items;                   // reused host staging of the work-item table
@@ -194,7 +194,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
+  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
                     &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
@@ -286,6 +286,7 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   CK(ctx->desc.ensure(static_cast<size_t>(rows) * kDim));
   CK(ctx->norm.ensure(static_cast<size_t>(rows) * 4));
   CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
+  CK(ctx->gmin8.ensure(static_cast<size_t>(rows) / 8 * 4 + 64));
   CK(ctx->flags.ensure(4));
   CK(ctx->img_min.ensure(4 * static_cast<size_t>(n_img)));
   CK(cudaMemsetAsync(ctx->img_min.p, 0x7f, 4 * static_cast<size_t>(n_img), ctx->stream));
@@ -300,9 +301,9 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
     const size_t bytes = static_cast<size_t>(n_desc[i]) * kDim * elt;
     if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_pack_rows(f32, st, n_desc[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
-                        ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(),
+                        ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                         ctx->flags.as<uint32_t>(), ctx->img_min.as<int32_t>() + i, ctx->stream));
-    ctx->launches += 2;
+    ctx->launches += 3;
   }
   uint32_t flags = 0;
   ctx->img_min_norm.assign(n_img, 0);
@@ -383,7 +384,8 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(int2) * n_items, cudaMemcpyHostToDevice,
                        ctx->stream));
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->norm.as<int32_t>(),
+  CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
+                 ctx->norm.as<int32_t>(),
                  ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(), static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
   if (n_items > 0) ctx->launches += 1;
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));

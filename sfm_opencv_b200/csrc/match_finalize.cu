@@ -71,6 +71,17 @@ __global__ void pad_rows_kernel(int n, int n_pad, int row0, int32_t* __restrict_
   }
 }
 
+// min |row|^2 of every group of 8 bank rows (padding rows carry the sentinel): the bound the
+// kNN epilogue compares raw dot products against
+__global__ void group_min_kernel(const int32_t* __restrict__ norm, int row0, int n_pad,
+                                 int32_t* __restrict__ gmin8) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 8 >= n_pad) return;
+  const int4 a = *reinterpret_cast<const int4*>(norm + row0 + g * 8);
+  const int4 b = *reinterpret_cast<const int4*>(norm + row0 + g * 8 + 4);
+  gmin8[row0 / 8 + g] = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
+}
+
 // ------------------------------------------------------------------------------- filter
 __device__ __forceinline__ bool ratio_fails(float d0, float d1, double ratio) {
   // `knn[i][0].distance > 0.6 * knn[i][1].distance`: float promoted to double (:884, :900)
@@ -223,8 +234,8 @@ __global__ void knn_to_float_kernel(const Knn2* __restrict__ knn, int64_t n,
 
 // ------------------------------------------------------------------------------- launchers
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
-                             int32_t* norm, int32_t* ckey, uint32_t* flags, int32_t* min_norm,
-                             cudaStream_t s) {
+                             int32_t* norm, int32_t* ckey, int32_t* gmin8, uint32_t* flags,
+                             int32_t* min_norm, cudaStream_t s) {
   if (n > 0) {
     const int warps = 8;
     const int grid = (n + warps - 1) / warps;
@@ -237,6 +248,7 @@ cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t
   }
   const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
   if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 255) / 256, 256, 0, s>>>(n, n_pad, row0, norm, ckey);
+  if (n_pad > 0) group_min_kernel<<<(n_pad / 8 + 255) / 256, 256, 0, s>>>(norm, row0, n_pad, gmin8);
   return cudaGetLastError();
 }
 

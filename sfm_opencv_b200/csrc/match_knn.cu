@@ -24,8 +24,9 @@
 // Epilogue = exact running top-2 per row, organised around the measured budget of ~1 ALU
 // op per accumulator (tools/ubench.cu): the fast path looks only at RAW dot products.
 // A column j can enter a row's top-2 only if |t_j|^2 - 2 q.t_j < v2 (v2 = second-best value so
-// far), hence only if q.t_j > (min_j |t_j|^2 - v2) / 2 =: thr.  Per group of 8 columns: a
-// 3-input-max tree (0.5 op/element) and one warp vote against the rows' thr.  Only groups in
+// far), hence only if 2 q.t_j - n8 > -v2, where n8 = min |t|^2 over the 8-column group of j
+// (precomputed at upload).  Per group of 8 columns: a 3-input-max tree (0.5 op/element),
+// one IMAD and one warp vote against the rows' bound.  Only groups in
 // which some row of the warp passes get their exact packed keys built (8 IMADs with the
 // column keys staged in shared memory) and inserted (20 min/max); that is harmless for the
 // rows that did not pass.  Skipped columns provably have two predecessors that beat them,
@@ -61,6 +62,7 @@ constexpr uint32_t kABytes = kTileM * kDim;     // 32 KB
 constexpr uint32_t kAHalfBytes = kHalfM * kDim; // 16 KB
 constexpr uint32_t kBBytes = kTileN * kDim;     // 16 KB
 constexpr uint32_t kCkBytes = kTileN * 4;       // 512 B
+constexpr uint32_t kGmBytes = kTileN / 8 * 4;   // 64 B: min |t|^2 of each 8-column group
 
 // What the producer tells the MMA and epilogue warps about an item.
 struct ItemInfo {
@@ -77,7 +79,8 @@ struct ItemInfo {
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + 2 * kABytes;
 constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
-constexpr uint32_t kOffInfo = kOffCk + kCkSlots * kCkBytes;
+constexpr uint32_t kOffGm = kOffCk + kCkSlots * kCkBytes;
+constexpr uint32_t kOffInfo = kOffGm + kCkSlots * kGmBytes;
 constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
 constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int2
 constexpr uint32_t kOffBar = kOffShare + kTileM * 16;
@@ -118,7 +121,7 @@ __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
 struct RowTop2 {
   int g1v, g1i, g2v, g2i;   // best / second best of the finished windows: value = |t|^2 - 2 q.t
   int m1, m2;               // top-2 of the current 256-column window as packed keys
-  int thr;                  // q.t must exceed this to matter: (nt_min - second best) >> 1
+  int thr;                  // a group matters iff 2 max(q.t) - min|t|^2 > thr; thr = -second best
 };
 
 __device__ __forceinline__ bool lex_lt(int v, int i, int gv, int gi) {
@@ -154,7 +157,7 @@ __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr
 //            eight 3-input-max trees and votes are issued before any insert, so they overlap.
 template <int kMode>
 __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint32_t (&r1)[32],
-                                            uint32_t ck_addr, int nt_min, RowTop2& s) {
+                                            uint32_t ck_addr, uint32_t gm_addr, RowTop2& s) {
   if constexpr (kMode == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) group_insert(&r0[8 * j], ck_addr + 32 * j, s);
@@ -162,13 +165,15 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
     for (int j = 0; j < 4; ++j) group_insert(&r1[8 * j], ck_addr + 128 + 32 * j, s);
   } else {
     bool h[8];
+    const int4 n0 = lds_v4(gm_addr), n1 = lds_v4(gm_addr + 16);
+    const int n8[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t* r = j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)];
       const int a = __vimax3_s32(r[0], r[1], r[2]);
       const int b = __vimax3_s32(r[3], r[4], r[5]);
       const int gm = max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
-      h[j] = __any_sync(0xffffffffu, gm > s.thr);
+      h[j] = __any_sync(0xffffffffu, gm * 2 - n8[j] > s.thr);
     }
     bool any = false;
 #pragma unroll
@@ -181,7 +186,7 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
     if (any) {
       // the window's second best also bounds what can still enter (values, not keys)
       const int w2 = s.m2 >> (kKeyShift + 1);
-      if (w2 < (1 << 22)) s.thr = max(s.thr, (nt_min - w2) >> 1);
+      if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
     }
   }
 }
@@ -189,15 +194,19 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
 template <int kMode>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ ckey,
-            const int32_t* __restrict__ norm, const PairDesc* __restrict__ pairs,
+            const int32_t* __restrict__ gmin8, const int32_t* __restrict__ norm, const PairDesc* __restrict__ pairs,
             const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // opaque to ptxas from here on: keep the base in a register instead of re-deriving it from
+  // the CTA's shared window (4 ALU instructions) in front of every shared-memory access
+  asm volatile("" : "+r"(smem_base));
 
   const uint32_t sA = smem_base + kOffA;
   const uint32_t sB = smem_base + kOffB;
   const uint32_t sCk = smem_base + kOffCk;
+  const uint32_t sGm = smem_base + kOffGm;
   const uint32_t bar0 = smem_base + kOffBar;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
@@ -289,9 +298,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             if (dbg & 1) {                       // timing experiment: no operand traffic
               mbar_arrive(bar_full(stage));
             } else {
-              mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes);
+              mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes + kGmBytes);
               tma_load_2d(sB + stage * kBBytes, &tmap, bar_full(stage), 0, row);
               bulk_load_1d(sCk + (tile_seq % kCkSlots) * kCkBytes, ckey + row, kCkBytes,
+                           bar_full(stage));
+              bulk_load_1d(sGm + (tile_seq % kCkSlots) * kGmBytes, gmin8 + row / 8, kGmBytes,
                            bar_full(stage));
             }
           }
@@ -358,7 +369,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
     uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
-      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, -1};
+      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN};
       int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0;
       int64_t knn_row = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -410,8 +421,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-          const uint32_t ck_addr = sCk + (tile_seq % kCkSlots) * kCkBytes + chalf * (kColsPerThread * 4);
-          tile_update<kMode>(r0, r1, ck_addr, nt_min, st);
+          const uint32_t slot = tile_seq % kCkSlots;
+          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
+          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
+          tile_update<kMode>(r0, r1, ck_addr, gm_addr, st);
           if ((t & 1) || t == ntiles - 1) {
             // close the 256-column window: merge its packed top-2 into the (value, index)
             // pairs, then tighten the bound, also with the row partner's second best
@@ -426,7 +439,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
               const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
               if (o.x == item && o.y < (1 << 22)) bound = min(bound, o.y + 1);
             }
-            st.thr = bound < (1 << 22) ? (nt_min - bound) >> 1 : -1;
+            st.thr = bound < (1 << 22) ? -bound : INT32_MIN;
           }
         }
         ++tile_seq;
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int variant)
 
 // mode 0: unfiltered exact top-2 epilogue; mode 1: threshold-filtered (default, same results)
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
-                        const int32_t* norm, const PairDesc* pairs, const int2* items,
+                        const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream) {
   const int dbg = mode >> 4;   // timing experiments (results invalid), see tools/exp_modes.py
   mode &= 15;
@@ -576,19 +589,19 @@ cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
   if (mode == 4)
-    knn2_kernel<4><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+    knn2_kernel<4><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   else if (mode == 2)
-    knn2_kernel<2><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+    knn2_kernel<2><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   else if (mode == 3)
-    knn2_kernel<3><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+    knn2_kernel<3><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   else if (mode == 0)
-    knn2_kernel<0><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+    knn2_kernel<0><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   else
-    knn2_kernel<1><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, norm, pairs, items,
+    knn2_kernel<1><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   return cudaGetLastError();
 }
