@@ -55,7 +55,7 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
   if (lane == 0) {
     atomicMin(min_norm, s);
     norm[row0 + r] = s;
-    ckey[row0 + r] = (s << (kKeyShift + 1)) | (r & (2 * kTileN - 1));
+    ckey[row0 + r] = (s << kColBits) | (r & ((1 << kColBits) - 1));
   }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (bad && lane == 0) atomicOr(flags, bad);
@@ -67,7 +67,7 @@ __global__ void pad_rows_kernel(int n, int n_pad, int row0, int32_t* __restrict_
   const int r = n + blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_pad) {
     norm[row0 + r] = kNormPad;
-    ckey[row0 + r] = (kNormPad << (kKeyShift + 1)) | (r & (2 * kTileN - 1));
+    ckey[row0 + r] = (kNormPad << kColBits) | (r & ((1 << kColBits) - 1));
   }
 }
 

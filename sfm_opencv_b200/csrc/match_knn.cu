@@ -32,7 +32,7 @@
 // rows that did not pass.  Skipped columns provably have two predecessors that beat them,
 // so results are identical to the unfiltered epilogue (SFM_KNN_MODE=0); a GPU test compares
 // the two bit for bit.  The two threads that share a row (column halves) exchange their
-// second-best value through shared memory once per 256-column window to tighten thr.
+// second-best value through shared memory once per 512-column window to tighten thr.
 // The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -97,10 +97,10 @@ __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
   a2 = __vimin3_s32(t, a2, b2);
 }
 
-// Packed key of accumulator r (= q.t) and column key ck = (|t|^2 << 8) | (train row & 255):
-// ((|t|^2 - 2 q.t) << 8) | column, one IMAD; orders like (distance, lower column first).
+// Packed key of accumulator r (= q.t) and column key ck = (|t|^2 << 9) | (train row & 511):
+// ((|t|^2 - 2 q.t) << 9) | column, one IMAD; orders like (distance, lower column first).
 __device__ __forceinline__ int make_key(uint32_t r, int ck) {
-  return static_cast<int>(r) * -(2 << (kKeyShift + 1)) + ck;
+  return static_cast<int>(r) * -(2 << kColBits) + ck;   // wraps, true value fits
 }
 
 // Exact top-2 of 8 keys merged into (m1, m2): pair-sort + merge tree, 20 min/max.
@@ -120,7 +120,7 @@ __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
 // Running state of one epilogue thread (one query row, half of the columns).
 struct RowTop2 {
   int g1v, g1i, g2v, g2i;   // best / second best of the finished windows: value = |t|^2 - 2 q.t
-  int m1, m2;               // top-2 of the current 256-column window as packed keys
+  int m1, m2;               // top-2 of the current 512-column window as packed keys
   int thr;                  // a group matters iff 2 max(q.t) - min|t|^2 > thr; thr = -second best
 };
 
@@ -185,7 +185,7 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
     }
     if (any) {
       // the window's second best also bounds what can still enter (values, not keys)
-      const int w2 = s.m2 >> (kKeyShift + 1);
+      const int w2 = s.m2 >> kColBits;
       if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
     }
   }
@@ -425,12 +425,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
           const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
           tile_update<kMode>(r0, r1, ck_addr, gm_addr, st);
-          if ((t & 1) || t == ntiles - 1) {
-            // close the 256-column window: merge its packed top-2 into the (value, index)
+          if ((t & 3) == 3 || t == ntiles - 1) {
+            // close the 512-column window: merge its packed top-2 into the (value, index)
             // pairs, then tighten the bound, also with the row partner's second best
-            const int base = (t & ~1) * kTileN;
-            insert_vi(st, st.m1 >> (kKeyShift + 1), base + (st.m1 & (2 * kTileN - 1)));
-            insert_vi(st, st.m2 >> (kKeyShift + 1), base + (st.m2 & (2 * kTileN - 1)));
+            const int base = (t & ~3) * kTileN;
+            insert_vi(st, st.m1 >> kColBits, base + (st.m1 & ((1 << kColBits) - 1)));
+            insert_vi(st, st.m2 >> kColBits, base + (st.m2 & ((1 << kColBits) - 1)));
             st.m1 = INT32_MAX;
             st.m2 = INT32_MAX;
             int bound = st.g2v;

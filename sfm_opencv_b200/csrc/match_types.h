@@ -7,9 +7,10 @@ namespace sfm {
 constexpr int kDim = 128;          // SIFT descriptor length in bytes (u8)
 constexpr int kTileM = 256;        // query rows per work item (two 128-lane TMEM halves)
 constexpr int kTileN = 128;        // train rows per B tile (TMEM columns per half)
-constexpr int kKeyShift = 7;       // log2(kTileN); packed key = (|t|^2 - 2 q.t) << 8 | (train row & 255)
+constexpr int kColBits = 9;        // packed key = (|t|^2 - 2 q.t) << 9 | (train row & 511): a
+                                   // key window is 4 train tiles; |value| < 2^21 keeps it in int32
 constexpr int kRowPad = 256;       // every image is padded to a multiple of this many rows
-constexpr int kNormPad = 0x7FFFFF; // norm^2 sentinel of padding rows (never selected)
+constexpr int kNormPad = 0x3FFFFF; // norm^2 sentinel of padding rows (never selected; << 9 fits)
 
 // One image pair of sfm_match_pairs.
 struct PairDesc {
