@@ -51,7 +51,7 @@ constexpr int kMmaWarps = 4;                    // (query half, tile parity)
 constexpr int kFirstEpiWarp = kFirstMmaWarp + kMmaWarps;
 constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
 constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;       // 768
-constexpr int kRegsCtl = 40;                    // setmaxnreg: producer / MMA warpgroups
+constexpr int kRegsCtl = 48;                    // setmaxnreg: producer / MMA warpgroups
 constexpr int kRegsEpi = 96;                    // setmaxnreg: epilogue warpgroups
 static_assert(8 * kRegsCtl + 16 * kRegsEpi <= 24 * 80, "register pool of the CTA (768 x 80)");
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
