@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(512, 1) alu_kernel(int iters, int a0, int b0, 
         }
         if (KIND == 8) asm volatile("mad.lo.s32 %0, %0, -256, %1;" : "+r"(x[k]) : "r"(y[k]));
         if (KIND == 9) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; selp.s32 %0, %2, %0, p;}" : "+r"(x[k]) : "r"(y[k]), "r"(y[(k + 1) & 7]));
+        if (KIND == 11) { unsigned b; asm volatile("{.reg .pred p; setp.lt.s32 p, %1, %2; vote.sync.ballot.b32 %0, p, 0xffffffff;}" : "=r"(b) : "r"(x[k]), "r"(y[k])); x[k] += b; }
+        if (KIND == 12) { unsigned b; asm volatile("{.reg .pred p, q; setp.lt.s32 p, %1, %2; vote.sync.any.pred q, p, 0xffffffff; selp.u32 %0, 1, 0, q;}" : "=r"(b) : "r"(x[k]), "r"(y[k])); x[k] += b; }
+        if (KIND == 13) { unsigned b; asm volatile("redux.sync.or.b32 %0, %1, 0xffffffff;" : "=r"(b) : "r"(x[k])); x[k] += b; }
         if (KIND == 10) asm volatile("{.reg .s32 t, u; max.s32 t, %0, %2; min.s32 %0, %0, %2; min.s32 u, t, %1; min.s32 %1, u, %3;}" : "+r"(x[k]), "+r"(y[k]) : "r"(y[(k + 1) & 7]), "r"(y[(k + 2) & 7]));
       }
     }
@@ -121,13 +124,13 @@ int main() {
     }
   }
   const char* names[] = {"imad", "min2", "min3", "addmin", "xor", "iadd3", "ffma", "imad_halfmin3",
-                         "imad_imm", "setp_selp", "merge_top2"};
+                         "imad_imm", "setp_selp", "merge_top2", "ballot", "vote_any", "redux_or"};
   for (int warps : {4, 8, 16}) {
-    for (int kind = 0; kind < 11; ++kind) {
+    for (int kind = 0; kind < 14; ++kind) {
       const int it = 2000;
       for (int rep = 0; rep < 2; ++rep) {
 #define RUN(K) case K: alu_kernel<K><<<n_sms, warps * 32>>>(it, 3, 5, cyc, (int*)sink); break;
-        switch (kind) { RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) }
+        switch (kind) { RUN(0) RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) RUN(9) RUN(10) RUN(11) RUN(12) RUN(13) }
       }
       if (cudaDeviceSynchronize() != cudaSuccess) { printf(", \"error\": \"alu\"}\n"); return 1; }
       const double c = (double)maxcyc(cyc, n_sms);
