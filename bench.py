@@ -289,6 +289,13 @@ def run_b200(args, rank, local_rank, world):
     my_ops = 2.0 * 128 * sum(n_desc[a] * n_desc[b] for a, b in my_pairs)
     tops = my_ops * args.steps / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else 0.0
     probe = ctx.probe_i8_peak(4000)                          # bare tcgen05 kind::i8 issue rate
+    traffic = None                                           # ncu DRAM bytes per launch, if captured
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "knn2_traffic.json")))
+        if (tj["images"], tj["desc_per_image"], tj["n_gpus"]) == (args.images, args.desc, world):
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
 
     # ---- e2e: host CV_32F matrices in, host DMatch lists out, every step ----------------
     ids = sorted({i for p in my_pairs for i in p})
@@ -357,7 +364,9 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "knn2_kernel", "achieved": tops,
                      "peak": INT8_DENSE_TOPS, "unit": "TOP/s", "frac": tops / INT8_DENSE_TOPS,
-                     "traffic": None,
+                     "traffic": traffic,
+                     "traffic_note": "DRAM bytes of one knn2 launch from profiles/knn2_traffic.json "
+                                     "(ncu --set full); null when the workload differs",
                      "peak_source": "B200 dense int8 datasheet (MEASURED_PEAKS.json has no int8 "
                                     "row); see measured_i8_probe_tops for the bare "
                                     "tcgen05.mma.kind::i8 rate measured in this run",

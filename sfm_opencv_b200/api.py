@@ -258,6 +258,34 @@ def build_projection(K, R, T) -> np.ndarray:
     return (np.asarray(K, np.float64).astype(np.float32) @ RT).astype(np.float32)
 
 
+def enumerate_observations(inds_2d_to_3d, keypoints_xy):
+    """Residual-block order of bundle_adjustment(), NViewReconstuct.cpp:1187-1211 (host glue):
+    for img in 0..n-1, for kp in order: if inds_2d_to_3d[img][kp] >= 0 -> one observation
+    (camera img, point id, kp.pt).  Returns (cam_idx i32, pt_idx i32, obs_xy f32[n,2])."""
+    cam, pt, obs = [], [], []
+    for img, (ids, kps) in enumerate(zip(inds_2d_to_3d, keypoints_xy)):
+        ids = np.asarray(ids).reshape(-1)
+        sel = np.nonzero(ids >= 0)[0]
+        cam.append(np.full(sel.size, img, np.int32))
+        pt.append(ids[sel].astype(np.int32))
+        obs.append(np.asarray(kps, np.float32).reshape(-1, 2)[sel])
+    if not cam:
+        return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 2), np.float32)
+    return np.concatenate(cam), np.concatenate(pt), np.concatenate(obs).astype(np.float32)
+
+
+def bundle_adjustment_residuals(ctx: Context, intrinsic, extrinsics, inds_2d_to_3d, keypoints_xy,
+                                pts3d, huber_delta=4.0):
+    """Evaluates every ReprojectCost block that bundle_adjustment() (NViewReconstuct.cpp:1162-1244)
+    hands to Ceres, in its order: returns (residuals [n_obs,2], cost = 0.5*sum rho(|r|^2) with
+    HuberLoss(huber_delta) as at :1184, rmse = sqrt(cost / n_obs) as printed at :1237-1238)."""
+    cam, pt, obs = enumerate_observations(inds_2d_to_3d, keypoints_xy)
+    r, cost = ctx.reproject_residuals(intrinsic, extrinsics, pts3d, cam, pt, obs,
+                                      huber_delta=huber_delta)
+    n = max(len(cam), 1)
+    return r, cost, float(np.sqrt(cost / n))
+
+
 def reconstruct(ctx: Context, K, R1, T1, R2, T2, p1, p2):
     """reconstruct(K,R1,T1,R2,T2,p1,p2,structure), NViewReconstuct.cpp:1117: returns structure
     [N,3] float64 (Point3d); raises on empty input where the reference returns -1."""

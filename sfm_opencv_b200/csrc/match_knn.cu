@@ -83,27 +83,12 @@ constexpr uint32_t kOffGm = kOffCk + kCkSlots * kCkBytes;
 constexpr uint32_t kOffInfo = kOffGm + kCkSlots * kGmBytes;
 constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
 constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int2
-// mode 5 (drain warps): per epilogue warp an event ring + control words, per epilogue
-// thread the drain-owned running top-2
-constexpr int kExactTiles = 2;                             // tiles of a sweep done unfiltered
-constexpr int kQueueSlots = 32;                            // events per ring (power of two)
-constexpr uint32_t kQAcc = 0;                              // [32 slots][8] raw accumulators
-constexpr uint32_t kQMeta = kQAcc + kQueueSlots * 32;      // [32] bank row | owner lane << 26
-constexpr uint32_t kQCommit = kQMeta + kQueueSlots * 4;    // events published by the epilogue warp
-constexpr uint32_t kQRead = kQCommit + 4;                  // events consumed by the drain warp
-constexpr uint32_t kQRow0 = kQRead + 4;                    // bank row of the train image
-constexpr uint32_t kQReserve = kQRow0 + 4;                 // ring positions handed out so far
-constexpr uint32_t kQBytes = kQReserve + 4;
-constexpr int kRowBits = 26;                               // bank rows < 2^26
-constexpr uint32_t kOffQueue = kOffShare + kTileM * 16;
-constexpr uint32_t kOffState = kOffQueue + kEpiWarps * kQBytes;        // 512 x int4
-constexpr uint32_t kOffDone = kOffState + kEpiWarps * 32 * 16;
-constexpr uint32_t kOffBar = kOffDone + 16;
+constexpr uint32_t kOffBar = kOffShare + kTileM * 16;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kKnnSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
 static_assert(kKnnSmemBytes <= 227 * 1024, "shared memory budget");
-static_assert(sizeof(ItemInfo) == 32 && kQBytes % 16 == 0, "smem layout");
+static_assert(sizeof(ItemInfo) == 32, "smem layout");
 
 // (a1 <= a2), (b1 <= b2) -> the two smallest of the four, sorted.
 __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
@@ -165,144 +150,6 @@ __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr
   insert8(k, s.m1, s.m2);
 }
 
-// ---- mode 5: the exact work is done by drain warps, the epilogue warps only filter --------
-// Epilogue side: groups that pass the bound are appended (raw accumulators + bank row +
-// owner lane) to the warp's ring; slots are assigned with a ballot, `wq` counts the events
-// of this warp (warp-uniform register), the drain's read counter gives back-pressure.
-__device__ __forceinline__ void queue_publish(uint32_t qa, uint32_t wq, int lane) {
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence_block();
-    sts_32_volatile(qa + kQCommit, wq);
-  }
-}
-
-// Straight-line, branch-free append of one 8-column group: when the group's score beats the
-// bound, the lane reserves a ring position with a shared-memory atomic and stores its event;
-// every instruction is predicated, nothing diverges.  A position that would overrun the
-// drain's (cached) read position is not written -- the caller detects that from the counter
-// afterwards and replays the tile through the waiting slow path.
-__device__ __forceinline__ void group_append_pred(int score, int thr, uint32_t qa, uint32_t rd,
-                                                  const uint32_t* r, uint32_t meta) {
-  static_assert(kQAcc == 0, "ring layout");
-  // every temporary is defined on both paths (pos = rd when the group does not pass), so
-  // ptxas has nothing to preserve across the predicated instructions
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .u32 pos, d, sl, a, m;\n\t"
-      "setp.gt.s32 p, %0, %1;\n\t"
-      "mov.u32 pos, %3;\n\t"
-      "@p atom.shared.add.u32 pos, [%2+%13], %15;\n\t"
-      "sub.u32 d, pos, %3;\n\t"
-      "setp.lt.and.u32 q, d, 32, p;\n\t"
-      "and.b32 sl, pos, 31;\n\t"
-      "mad.lo.u32 a, sl, 32, %2;\n\t"
-      "mad.lo.u32 m, sl, 4, %2;\n\t"
-      "@q st.shared.v4.b32 [a], {%4, %5, %6, %7};\n\t"
-      "@q st.shared.v4.b32 [a+16], {%8, %9, %10, %11};\n\t"
-      "@q st.shared.b32 [m+%14], %12;\n\t"
-      "}"
-      ::"r"(score), "r"(thr), "r"(qa), "r"(rd), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
-        "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(meta), "n"(kQReserve), "n"(kQMeta),
-        "r"(1)
-      : "memory");
-}
-
-__device__ __forceinline__ void filter_chunk_pred(const uint32_t (&r)[32], uint32_t gm_addr,
-                                                  int thr, uint32_t qa, uint32_t rd,
-                                                  uint32_t meta0) {
-  const int4 nn = lds_v4(gm_addr);
-  const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-    const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-    const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
-    group_append_pred(gm * 2 - n8[j], thr, qa, rd, &r[8 * j], meta0 + 8 * j);
-  }
-}
-
-// Replay of a chunk whose events did not all fit: the reservations of the failed attempt are
-// rolled back by the caller; here every group waits for ring space (warp-uniform), so
-// nothing can be lost.
-__device__ __forceinline__ void chunk_filter_append_slow(const uint32_t (&r)[32],
-                                                         uint32_t gm_addr, uint32_t qa,
-                                                         uint32_t& wq, uint32_t meta0, int lane,
-                                                         int thr) {
-  const int4 nn = lds_v4(gm_addr);
-  const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-    const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-    const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
-    const bool p = gm * 2 - n8[j] > thr;
-    const uint32_t hit = __ballot_sync(0xffffffffu, p);
-    if (hit) {
-      const uint32_t n = __popc(hit);
-      uint32_t spins = 0;
-      while (static_cast<int>(wq + n - static_cast<uint32_t>(lds_32_volatile(qa + kQRead))) >
-             kQueueSlots) {
-        queue_publish(qa, wq, lane);
-        spin_guard(spins, 1);
-      }
-      if (p) {
-        const uint32_t slot = (wq + __popc(hit & ((1u << lane) - 1u))) & (kQueueSlots - 1);
-        sts_v4(qa + kQAcc + slot * 32, r[8 * j + 0], r[8 * j + 1], r[8 * j + 2], r[8 * j + 3]);
-        sts_v4(qa + kQAcc + slot * 32 + 16, r[8 * j + 4], r[8 * j + 5], r[8 * j + 6],
-               r[8 * j + 7]);
-        sts_32(qa + kQMeta + slot * 4, meta0 + 8 * j);
-      }
-      wq += n;
-    }
-  }
-}
-
-// Drain side: one batch of up to 32 committed events, one per lane, possibly from several
-// rings: lane's event = ring at qa, position pos; state_base = shared address of the 32
-// running top-2 entries of that ring's epilogue warp; skey = a key unique per ring.
-__device__ __forceinline__ void drain_batch(bool has, uint32_t qa, uint32_t state_base,
-                                            uint32_t pos, uint32_t skey, int lane,
-                                            const int32_t* __restrict__ ckey) {
-  int v1 = INT32_MAX, i1 = INT32_MAX, v2 = INT32_MAX, i2 = INT32_MAX;
-  uint32_t owner = 0;
-  if (has) {
-    const uint32_t slot = pos & (kQueueSlots - 1);
-    const uint32_t meta = static_cast<uint32_t>(lds_32(qa + kQMeta + slot * 4));
-    const int row = static_cast<int>(meta & ((1u << kRowBits) - 1));
-    owner = meta >> kRowBits;
-    const int4 a0 = lds_v4(qa + kQAcc + slot * 32), a1 = lds_v4(qa + kQAcc + slot * 32 + 16);
-    const int4 c0 = __ldg(reinterpret_cast<const int4*>(ckey + row));
-    const int4 c1 = __ldg(reinterpret_cast<const int4*>(ckey + row) + 1);
-    int k[8];
-    k[0] = make_key(a0.x, c0.x); k[1] = make_key(a0.y, c0.y);
-    k[2] = make_key(a0.z, c0.z); k[3] = make_key(a0.w, c0.w);
-    k[4] = make_key(a1.x, c1.x); k[5] = make_key(a1.y, c1.y);
-    k[6] = make_key(a1.z, c1.z); k[7] = make_key(a1.w, c1.w);
-    int e1 = INT32_MAX, e2 = INT32_MAX;
-    insert8(k, e1, e2);
-    const int base = (row - lds_32(qa + kQRow0)) & ~((1 << kColBits) - 1);
-    v1 = e1 >> kColBits; i1 = base + (e1 & ((1 << kColBits) - 1));
-    v2 = e2 >> kColBits; i2 = base + (e2 & ((1 << kColBits) - 1));
-  }
-  // events of the same owner are applied one per round (read-modify-write of its entry)
-  const uint32_t peers = __match_any_sync(0xffffffffu, has ? skey * 32u + owner : 0x10000u + lane);
-  const int rank = __popc(peers & ((1u << lane) - 1u));
-  const int rounds = __reduce_max_sync(0xffffffffu, has ? __popc(peers) : 0);
-  for (int r = 0; r < rounds; ++r) {
-    if (has && rank == r) {
-      const uint32_t sa = state_base + owner * 16;
-      const int4 cur = lds_v4(sa);
-      RowTop2 s = {cur.x, cur.y, cur.z, cur.w, 0, 0, 0};
-      insert_vi(s, v1, i1);
-      insert_vi(s, v2, i2);
-      sts_v4(sa, s.g1v, s.g1i, s.g2v, s.g2i);
-    }
-    __syncwarp();
-  }
-}
-
 // Top-2 update with the thread's 64 columns of one tile (two 32-column chunks);
 // ck_addr = shared address of their keys.
 //   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
@@ -342,20 +189,6 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
       if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
     }
   }
-}
-
-// The unfiltered first tiles of a sweep in mode 5, kept out of line so that the filtered
-// steady-state loop stays small in the instruction cache.
-__device__ __noinline__ void exact_tile_mode5(uint32_t ta, uint32_t bar_empty_addr, int lane,
-                                              uint32_t ck_addr, uint32_t gm_addr, RowTop2& st) {
-  uint32_t r0[32], r1[32];
-  tmem_ld_x32(ta, r0);
-  tmem_ld_x32(ta + 32, r1);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar_empty_addr);
-  tile_update<0>(r0, r1, ck_addr, gm_addr, st);
 }
 
 template <int kMode>
@@ -409,12 +242,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
   }
   if (threadIdx.x < kTileM)    // (item tag, second-best value) slots of the row-sharing threads
     sts_v4(smem_base + kOffShare + threadIdx.x * 16, 0xffffffffu, 0, 0xffffffffu, 0);
-  if (threadIdx.x < kEpiWarps * 32)
-    sts_v4(smem_base + kOffState + threadIdx.x * 16, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
-  if (threadIdx.x < kEpiWarps) {
-    sts_v4(smem_base + kOffQueue + threadIdx.x * kQBytes + kQCommit, 0, 0, 0, 0);
-    if (threadIdx.x == 0) sts_32(smem_base + kOffDone, 0);
-  }
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -487,60 +314,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           }
         }
       }
-    } else if (warp < kFirstMmaWarp) {
-      // ===================================================== drain warps (mode 5 only)
-      if constexpr (kMode == 5) {
-        const int d = warp - 1;                   // serves the epilogue warps e with e % 3 == d
-        uint32_t rd[6] = {0, 0, 0, 0, 0, 0};
-        uint32_t idle = 0;
-        while (!(dbg & 8)) {
-          // gather up to 32 committed events over this warp's rings, one per lane
-          int take[6], total = 0;
-#pragma unroll
-          for (int qi = 0; qi < 6; ++qi) {
-            const int e = d + 3 * qi;
-            take[qi] = 0;
-            if (e < kEpiWarps) {
-              const uint32_t c = static_cast<uint32_t>(
-                  lds_32_volatile(smem_base + kOffQueue + e * kQBytes + kQCommit));
-              take[qi] = min(static_cast<int>(c - rd[qi]), 32 - total);
-              total += take[qi];
-            }
-          }
-          if (total == 0) {
-            if (lds_32_volatile(smem_base + kOffDone) == kEpiWarps) break;
-            __nanosleep(100);
-            spin_guard(idle, 3);
-            continue;
-          }
-          idle = 0;
-          __threadfence_block();
-          uint32_t qa = 0, sb = 0, pos = 0, skey = 0;
-          int first = 0;
-#pragma unroll
-          for (int qi = 0; qi < 6; ++qi) {
-            if (lane >= first && lane < first + take[qi]) {
-              const int e = d + 3 * qi;
-              qa = smem_base + kOffQueue + e * kQBytes;
-              sb = smem_base + kOffState + e * 32 * 16;
-              pos = rd[qi] + (lane - first);
-              skey = e;
-            }
-            first += take[qi];
-          }
-          drain_batch(lane < total, qa, sb, pos, skey, lane, ckey);
-          __syncwarp();
-          __threadfence_block();
-#pragma unroll
-          for (int qi = 0; qi < 6; ++qi) {
-            if (take[qi] > 0) {
-              rd[qi] += take[qi];
-              if (lane == 0)
-                sts_32_volatile(smem_base + kOffQueue + (d + 3 * qi) * kQBytes + kQRead, rd[qi]);
-            }
-          }
-        }
-      }
     } else if (warp >= kFirstMmaWarp) {
       // ===================================================== MMA issuers: (half mh, parity mp)
       const uint32_t mh = (warp - kFirstMmaWarp) & 1, mp = (warp - kFirstMmaWarp) >> 1;
@@ -594,15 +367,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     const uint32_t share_own = smem_base + kOffShare + row_in_blk * 16 + chalf * 8;
     const uint32_t share_other = smem_base + kOffShare + row_in_blk * 16 + (chalf ^ 1) * 8;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
-    // mode 5: this warp's event ring, this thread's and its row partner's drain-owned entries
-    const uint32_t qa = smem_base + kOffQueue + e * kQBytes;
-    const uint32_t state_own = smem_base + kOffState + (e * 32 + lane) * 16;
-    const uint32_t state_other = smem_base + kOffState + ((e ^ 4) * 32 + lane) * 16;
-    uint32_t wq = 0, rdc = 0;                      // events appended / known consumed (uniform)
     uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
       RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN};
-      int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0, t_row0 = 0;
+      int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0;
       int64_t knn_row = 0;
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(bar_t_full(buf, half), bphase);
@@ -612,73 +380,32 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           rows_valid = info[abuf].rows_valid;
           norm_row = info[abuf].norm_row;
           nt_min = info[abuf].nt_min;
-          t_row0 = info[abuf].t_row0;
           knn_row = info[abuf].knn_row;
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(bar_a_empty(abuf));
-            if (kMode == 5) sts_32(qa + kQRow0, t_row0);   // published with the first events
-          }
+          if (lane == 0) mbar_arrive(bar_a_empty(abuf));
           abuf ^= 1;
         }
         const uint32_t ta = t_addr + buf * (2 * kTileN);
-        if constexpr (kMode >= 2 && kMode <= 4) {
+        if constexpr (kMode >= 2) {
           // timing experiments only (results are garbage):
           // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
-          if constexpr (kMode == 2) {
+          if constexpr (kMode == 2 || kMode == 4) {
             uint32_t r0[32], r1[32];
             tmem_ld_x32(ta, r0);
             tmem_ld_x32(ta + 32, r1);
             tmem_ld_wait();
             st.g1v = min(st.g1v, static_cast<int>(r0[0] ^ r1[31]));
-          }
-          if constexpr (kMode == 4) {
-            // fast-path anatomy: dbg bits add the ingredients of the real epilogue one by one
-            //   32: load / wait per chunk instead of both loads then one wait
-            //   64: bound from shared memory + per-group norms (LDS, IMAD)
-            //  128: real divergent branch with stores per group (never taken)
-            //  256: per-chunk __syncwarp + vote + shared-memory counter read
-            int thr = st.thr;
-            int n8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const uint32_t slot = tile_seq % kCkSlots;
-            const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
-            if (dbg & 64) {
-              const int og = lds_32(state_own + 8), pg = lds_32(state_other + 8);
-              thr = max(thr, -min(og, pg));
-              const int4 n0 = lds_v4(gm_addr), n1 = lds_v4(gm_addr + 16);
-              n8[0] = n0.x; n8[1] = n0.y; n8[2] = n0.z; n8[3] = n0.w;
-              n8[4] = n1.x; n8[5] = n1.y; n8[6] = n1.z; n8[7] = n1.w;
-            }
-            uint32_t r0[32], r1[32];
-            tmem_ld_x32(ta, r0);
-            if (dbg & 32) tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (c == 1) {
-                tmem_ld_x32(ta + 32, r1);
-                tmem_ld_wait();
-              }
-              bool ovf = false;
+            if constexpr (kMode == 4) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t* r = c == 0 ? &r0[8 * j] : &r1[8 * j];
-                const int a = __vimax3_s32(r[0], r[1], r[2]);
-                const int b = __vimax3_s32(r[3], r[4], r[5]);
-                const int gm = max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
-                if (dbg & 128) {
-                  if (gm * 2 - n8[4 * c + j] > thr + 0x40000000) {     // never true
-                    sts_v4(qa + kQAcc, r[0], r[1], r[2], r[3]);
-                    sts_v4(qa + kQAcc + 16, r[4], r[5], r[6], r[7]);
-                    ovf = true;
-                  }
-                } else if (gm * 2 - n8[4 * c + j] > thr) {
-                  st.g1i = gm; ++st.g2v;
-                }
-              }
-              if (dbg & 256) {
-                __syncwarp();
-                if (__any_sync(0xffffffffu, ovf)) st.g2i++;
-                st.g1v += lds_32(qa + kQReserve);
+                const int a = __vimax3_s32(r0[8 * j + 0], r0[8 * j + 1], r0[8 * j + 2]);
+                const int b = __vimax3_s32(r0[8 * j + 3], r0[8 * j + 4], r0[8 * j + 5]);
+                const int c = __vimax3_s32(r1[8 * j + 0], r1[8 * j + 1], r1[8 * j + 2]);
+                const int d = __vimax3_s32(r1[8 * j + 3], r1[8 * j + 4], r1[8 * j + 5]);
+                const int g0 = max(__vimax3_s32(a, b, r0[8 * j + 6]), static_cast<int>(r0[8 * j + 7]));
+                const int g1 = max(__vimax3_s32(c, d, r1[8 * j + 6]), static_cast<int>(r1[8 * j + 7]));
+                if (g0 > st.thr) { st.g1i = g0; ++st.g2v; }
+                if (g1 > st.thr) { st.g1i = g1; ++st.g2i; }
               }
             }
           }
@@ -686,60 +413,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
         } else {
-          const uint32_t slot = tile_seq % kCkSlots;
-          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
-          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
-          if constexpr (kMode == 5) {
-            if (t >= kExactTiles || (dbg & 16)) {
-              // filtered tile: one 32-register chunk at a time (the append path needs the
-              // registers), bound = second best of the row so far (either column half), read
-              // from the drain-owned entries; any earlier value of this item is a valid bound
-              const int og = lds_32(state_own + 8), pg = lds_32(state_other + 8);
-              int bound = og;
-              if (pg < (1 << 22)) bound = min(bound, pg + 1);
-              const int thr = (dbg & 4) ? INT32_MAX : (bound < (1 << 22) ? -bound : INT32_MIN);
-              const uint32_t meta0 =
-                  static_cast<uint32_t>(t_row0 + t * kTileN + chalf * kColsPerThread) |
-                  (static_cast<uint32_t>(lane) << kRowBits);
-              uint32_t r0[32], r1[32];
-              tmem_ld_x32(ta, r0);
-              tmem_ld_x32(ta + 32, r1);
-              tmem_ld_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-              filter_chunk_pred(r0, gm_addr, thr, qa, rdc, meta0);
-              filter_chunk_pred(r1, gm_addr + 16, thr, qa, rdc, meta0 + 32);
-              __syncwarp();
-              uint32_t nres = static_cast<uint32_t>(lds_32_volatile(qa + kQReserve));
-              if (static_cast<int>(nres - rdc) > kQueueSlots) {
-                // some events did not fit behind the cached read position: drop this tile's
-                // events (positions >= wq, unpublished) and replay it with the waiting path
-                __syncwarp();
-                if (lane == 0) sts_32(qa + kQReserve, wq);
-                __syncwarp();
-                chunk_filter_append_slow(r0, gm_addr, qa, wq, meta0, lane, thr);
-                chunk_filter_append_slow(r1, gm_addr + 16, qa, wq, meta0 + 32, lane, thr);
-                if (lane == 0) sts_32(qa + kQReserve, wq);
-                __syncwarp();
-                nres = wq;
-              }
-              if (nres != wq || static_cast<int>(nres - rdc) > kQueueSlots / 2) {
-                wq = nres;
-                queue_publish(qa, wq, lane);
-                rdc = static_cast<uint32_t>(lds_32_volatile(qa + kQRead));
-              }
-            } else {
-              // the first tiles of a sweep are done here, unfiltered; their result seeds
-              // the entry the drain warp continues with
-              exact_tile_mode5(ta, bar_t_empty(buf, half), lane, ck_addr, gm_addr, st);
-              if (t == kExactTiles - 1 || t == ntiles - 1) {
-                insert_vi(st, st.m1 >> kColBits, st.m1 & ((1 << kColBits) - 1));
-                insert_vi(st, st.m2 >> kColBits, st.m2 & ((1 << kColBits) - 1));
-                if (ntiles > kExactTiles) sts_v4(state_own, st.g1v, st.g1i, st.g2v, st.g2i);
-              }
-            }
-          } else {
           // pull this thread's 64 accumulators out of TMEM and hand the buffer back at once
           uint32_t r0[32], r1[32];
           tmem_ld_x32(ta, r0);
@@ -748,6 +421,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
+          const uint32_t slot = tile_seq % kCkSlots;
+          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
+          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
           tile_update<kMode>(r0, r1, ck_addr, gm_addr, st);
           if ((t & 3) == 3 || t == ntiles - 1) {
             // close the 512-column window: merge its packed top-2 into the (value, index)
@@ -765,25 +441,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             }
             st.thr = bound < (1 << 22) ? -bound : INT32_MIN;
           }
-          }
         }
         ++tile_seq;
         if (++buf == kAccBufs) {
           buf = 0;
           bphase ^= 1;
         }
-      }
-      if (kMode == 5 && ntiles > kExactTiles) {
-        // wait until the drain warp has applied every event of this sweep, take the entry
-        // over and reset it for the next item
-        queue_publish(qa, wq, lane);
-        uint32_t spins = 0;
-        while (static_cast<uint32_t>(lds_32_volatile(qa + kQRead)) != wq) spin_guard(spins, 2);
-        rdc = wq;
-        __threadfence_block();
-        const int4 f = lds_v4(state_own);
-        st.g1v = f.x; st.g1i = f.y; st.g2v = f.z; st.g2i = f.w;
-        sts_v4(state_own, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX);
       }
       // merge the two column halves of the row: the upper half hands its top-2 over
       const uint32_t slot = merge_addr + mslot * (kTileM * 16);
@@ -805,10 +468,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
               *reinterpret_cast<int4*>(&out);
         }
       }
-    }
-    if (kMode == 5) {
-      __syncwarp();
-      if (lane == 0) atoms_add(smem_base + kOffDone, 1);   // lets the drain warps leave
     }
   }
 
@@ -925,17 +584,11 @@ cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
     e = cudaFuncSetAttribute(knn2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kKnnSmemBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(knn2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
     configured = true;
   }
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
-  if (mode == 5)
-    knn2_kernel<5><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  else if (mode == 4)
+  if (mode == 4)
     knn2_kernel<4><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
                                                                  n_items, knn_out, dbg);
   else if (mode == 2)

@@ -52,7 +52,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(100000u)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -61,19 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 15)) {
+    if (++spins > (1u << 16)) {
       printf("sfm_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();
     }
-  }
-}
-
-// Bounded software spin (shared-memory flags): traps instead of hanging the GPU box.
-__device__ __forceinline__ void spin_guard(uint32_t& spins, int what) {
-  if (++spins > (1u << 24)) {
-    printf("sfm_b200: spin timeout block %d thread %d site %d\n", blockIdx.x, threadIdx.x, what);
-    __trap();
   }
 }
 
@@ -108,14 +100,6 @@ __device__ __forceinline__ int lds_32(uint32_t addr) {
   int v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
-}
-__device__ __forceinline__ int lds_32_volatile(uint32_t addr) {
-  int v;
-  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_32_volatile(uint32_t addr, uint32_t a) {
-  asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ int atoms_add(uint32_t addr, int v) {
   int old;

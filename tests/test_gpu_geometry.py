@@ -152,3 +152,18 @@ def test_config5_size_properties(ctx):
     shifted = (obs + np.float32(1.0)).astype(np.float64) - obs.astype(np.float64)
     assert np.abs((r - r2) - shifted).max() < 1e-9
     assert abs(cost - 0.5 * float((r ** 2).sum())) <= 1e-9 * max(1.0, cost)
+
+
+def test_bundle_adjustment_residuals_api(ctx):
+    """Reference-shaped call: blocks enumerated camera-major, Huber(4) cost, RMSE of :1237-1238."""
+    import sfm_opencv_b200 as sfm
+    sc = synth.scene(600, 3, seed=21, noise_px=3.0)
+    rng = np.random.default_rng(1)
+    ids = [np.where(rng.random(600) < 0.7, np.arange(600), -1) for _ in range(3)]
+    kps = [sc["xy"][v] for v in range(3)]
+    r, cost, rmse = sfm.bundle_adjustment_residuals(ctx, sc["intr"], sc["ext"], ids, kps, sc["X"])
+    cam, pt, obs = G.enumerate_observations(ids, kps)
+    rr = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+    assert r.shape == rr.shape and np.abs(r - rr).max() <= REL_TOL * max(1.0, np.abs(rr).max())
+    c = G.huber_cost(rr, 4.0)
+    assert abs(cost - c) <= 1e-9 * c and abs(rmse - np.sqrt(c / len(cam))) <= 1e-9

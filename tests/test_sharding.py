@@ -93,3 +93,18 @@ def test_gather_world2_gloo_equals_single_rank():
     for (a, b), (qi, ti) in zip(pairs, got):
         m, _, _, _, _ = M.match_features(bank[a], bank[b])
         assert qi == m[:, 0].tolist() and ti == m[:, 1].tolist()
+
+
+def test_enumerate_observations_is_camera_major():
+    """Host mirror of the residual-block enumeration (NViewReconstuct.cpp:1187-1211) against the
+    oracle's restatement; no GPU needed."""
+    import sfm_opencv_b200 as sfm
+    from oracle import geometry as G
+    rng = np.random.default_rng(3)
+    ids = [rng.integers(-1, 20, n) for n in (7, 0, 13, 5)]
+    kps = [rng.uniform(0, 1000, (len(i), 2)).astype(np.float32) for i in ids]
+    a = sfm.enumerate_observations(ids, kps)
+    b = G.enumerate_observations(ids, kps)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (np.diff(a[0]) >= 0).all() and len(a[0]) == sum(int((i >= 0).sum()) for i in ids)

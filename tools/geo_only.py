@@ -6,7 +6,7 @@ from oracle import synth
 ctx = sfm.Context(0)
 sc = synth.scene(4_000_000, 2)
 cam, pt = synth.observations_camera_major(4_000_000, 2)
-for _ in range(2):
+for _ in range(3):
     _, _, ms = ctx.triangulate_batch(sc["P"], sc["xy"], want_X4=True, want_xyz=False, iters=1)
     _, _, ms2 = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt,
                                         sc["xy"].reshape(-1, 2), want_cost=False, iters=1)

@@ -18,6 +18,6 @@ ncu --set full --clock-control none --import-source on -k regex:knn2 -s 3 -c 1 -
 echo "ncu knn2 rc=$?"
 GEO="python tools/geo_only.py"
 $GEO > gpurun_out/${TAG}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'triangulate_kernel|residual_kernel' -s 2 -c 2 -f -o gpurun_out/${TAG}_geo $GEO > gpurun_out/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'triangulate_kernel|residual_kernel' -s 2 -c 2 --kernel-name-base function -f -o gpurun_out/${TAG}_geo $GEO > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ncu geo rc=$?"
 ls -la gpurun_out | grep ${TAG}
