@@ -191,6 +191,36 @@ __device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint
   }
 }
 
+// Same for one 32-column chunk (4 groups); used by the software-pipelined loop, where the
+// next chunk's tcgen05.ld is in flight while this one is processed.
+template <int kMode>
+__device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
+                                             uint32_t gm_addr, RowTop2& s) {
+  if constexpr (kMode == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
+  } else {
+    const int4 nn = lds_v4(gm_addr);
+    const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
+    bool h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
+      const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
+      const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
+      h[j] = __any_sync(0xffffffffu, gm * 2 - n8[j] > s.thr);
+    }
+    if (h[0]) group_insert(&r[0], ck_addr, s);
+    if (h[1]) group_insert(&r[8], ck_addr + 32, s);
+    if (h[2]) group_insert(&r[16], ck_addr + 64, s);
+    if (h[3]) group_insert(&r[24], ck_addr + 96, s);
+    if (h[0] | h[1] | h[2] | h[3]) {
+      const int w2 = s.m2 >> kColBits;
+      if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
+    }
+  }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ ckey,
@@ -372,6 +402,63 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN};
       int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0;
       int64_t knn_row = 0;
+      if constexpr (kMode <= 1) {
+        // ---- software-pipelined sweep: a tile is two 32-column chunks per thread; the
+        // tcgen05.ld of the next chunk is in flight while the current one is processed, so
+        // the TMEM read latency is off the warp's per-tile instruction chain
+        mbar_wait(bar_t_full(buf, half), bphase);
+        tc_fence_after();
+        ntiles = info[abuf].ntiles;
+        rows_valid = info[abuf].rows_valid;
+        norm_row = info[abuf].norm_row;
+        nt_min = info[abuf].nt_min;
+        knn_row = info[abuf].knn_row;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_empty(abuf));
+        abuf ^= 1;
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(t_addr + buf * (2 * kTileN), ra);
+        tmem_ld_wait();
+        for (int t = 0; t < ntiles; ++t) {
+          const uint32_t ta = t_addr + buf * (2 * kTileN);
+          tmem_ld_x32(ta + 32, rb);                       // chunk 1 in flight
+          const uint32_t slot = tile_seq % kCkSlots;
+          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
+          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
+          chunk_update<kMode>(ra, ck_addr, gm_addr, st);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));   // tile t is out of TMEM
+          const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
+          if (t + 1 < ntiles) {
+            mbar_wait(bar_t_full(nbuf, half), nphase);
+            tc_fence_after();
+            tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1 in flight
+          }
+          chunk_update<kMode>(rb, ck_addr + 128, gm_addr + 16, st);
+          if (t + 1 < ntiles) tmem_ld_wait();
+          if ((t & 3) == 3 || t == ntiles - 1) {
+            // close the 512-column window: merge its packed top-2 into the (value, index)
+            // pairs, then tighten the bound, also with the row partner's second best
+            const int base = (t & ~3) * kTileN;
+            insert_vi(st, st.m1 >> kColBits, base + (st.m1 & ((1 << kColBits) - 1)));
+            insert_vi(st, st.m2 >> kColBits, base + (st.m2 & ((1 << kColBits) - 1)));
+            st.m1 = INT32_MAX;
+            st.m2 = INT32_MAX;
+            int bound = st.g2v;
+            if (kMode == 1) {
+              sts_v2(share_own, item, st.g2v);
+              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
+              if (o.x == item && o.y < (1 << 22)) bound = min(bound, o.y + 1);
+            }
+            st.thr = bound < (1 << 22) ? -bound : INT32_MIN;
+          }
+          ++tile_seq;
+          buf = nbuf;
+          bphase = nphase;
+        }
+      } else
       for (int t = 0; t < ntiles; ++t) {
         mbar_wait(bar_t_full(buf, half), bphase);
         tc_fence_after();
