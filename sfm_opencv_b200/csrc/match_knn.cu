@@ -103,18 +103,30 @@ __device__ __forceinline__ int make_key(uint32_t r, int ck) {
   return static_cast<int>(r) * -(2 << kColBits) + ck;   // wraps, true value fits
 }
 
-// Exact top-2 of 8 keys merged into (m1, m2): pair-sort + merge tree, 20 min/max.
+// Exact top-2 of 8 keys merged into (m1, m2).  The new minimum is a 3-input-min tree over
+// the nine candidates (4 ALU ops).  The new second is the minimum over the ten values with one
+// instance of that minimum knocked out: x -> x - min - 1 as UNSIGNED sends the minimum to
+// 2^32 - 1 and keeps the order of everything else (keys of a window are unique), so it is
+// another 3-input unsigned-min tree (5 ops) after ten subtractions, which ptxas places on
+// the otherwise idle FMA pipe (IMAD.IADD).  11 ALU ops instead of the 20 of a sorting network.
 __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
-  int lo[4], hi[4];
+  const int a = __vimin3_s32(k[0], k[1], k[2]);
+  const int b = __vimin3_s32(k[3], k[4], k[5]);
+  const int c = __vimin3_s32(k[6], k[7], m1);
+  const int lo = __vimin3_s32(a, b, c);
+  const uint32_t nlo = ~static_cast<uint32_t>(lo);          // x + ~lo == x - lo - 1 (mod 2^32)
+  uint32_t d[10];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lo[j] = min(k[2 * j], k[2 * j + 1]);
-    hi[j] = max(k[2 * j], k[2 * j + 1]);
-  }
-  merge_top2(lo[0], hi[0], lo[2], hi[2]);
-  merge_top2(lo[1], hi[1], lo[3], hi[3]);
-  merge_top2(lo[0], hi[0], lo[1], hi[1]);
-  merge_top2(m1, m2, lo[0], hi[0]);
+  for (int i = 0; i < 8; ++i) d[i] = static_cast<uint32_t>(k[i]) + nlo;
+  d[8] = static_cast<uint32_t>(m1) + nlo;
+  d[9] = static_cast<uint32_t>(m2) + nlo;
+  const uint32_t e0 = __vimin3_u32(d[0], d[1], d[2]);
+  const uint32_t e1 = __vimin3_u32(d[3], d[4], d[5]);
+  const uint32_t e2 = __vimin3_u32(d[6], d[7], d[8]);
+  const uint32_t e3 = __vimin3_u32(e0, e1, e2);
+  const uint32_t sec = min(e3, d[9]);
+  m1 = lo;
+  m2 = static_cast<int>(sec - nlo);                          // sec + lo + 1
 }
 
 // Running state of one epilogue thread (one query row, half of the columns).
