@@ -18,6 +18,9 @@ ncu --set full --clock-control none --import-source on -k regex:knn2 -s 3 -c 1 -
 echo "ncu knn2 rc=$?"
 GEO="python tools/geo_only.py"
 $GEO > gpurun_out/${TAG}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'triangulate_kernel|residual_kernel' -s 2 -c 2 --kernel-name-base function -f -o gpurun_out/${TAG}_geo $GEO > gpurun_out/${TAG}_ncu3.log 2>&1
-echo "ncu geo rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:triangulate_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_tri $GEO > gpurun_out/${TAG}_ncu3.log 2>&1
+echo "ncu tri rc=$?"
+$GEO > gpurun_out/${TAG}_plain4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:residual_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_res $GEO > gpurun_out/${TAG}_ncu4.log 2>&1
+echo "ncu res rc=$?"
 ls -la gpurun_out | grep ${TAG}
