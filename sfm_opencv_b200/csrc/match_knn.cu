@@ -32,7 +32,7 @@
 // rows that did not pass.  Skipped columns provably have two predecessors that beat them,
 // so results are identical to the unfiltered epilogue (SFM_KNN_MODE=0); a GPU test compares
 // the two bit for bit.  The two threads that share a row (column halves) exchange their
-// second-best value through shared memory once per 512-column window to tighten thr.
+// second-best value through shared memory once per 1024-column window to tighten the bound.
 // The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -51,9 +51,12 @@ constexpr int kMmaWarps = 4;                    // (query half, tile parity)
 constexpr int kFirstEpiWarp = kFirstMmaWarp + kMmaWarps;
 constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
 constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;       // 768
-constexpr int kRegsCtl = 48;                    // setmaxnreg: producer / MMA warpgroups
-constexpr int kRegsEpi = 96;                    // setmaxnreg: epilogue warpgroups
-static_assert(8 * kRegsCtl + 16 * kRegsEpi <= 24 * 80, "register pool of the CTA (768 x 80)");
+constexpr int kRegsProd = 24;                   // setmaxnreg: producer warpgroup (warps 0..3)
+constexpr int kRegsMma = 40;                    // setmaxnreg: MMA warpgroup (warps 4..7)
+constexpr int kRegsEpi = 104;                   // setmaxnreg: epilogue warpgroups
+static_assert(4 * kRegsProd + 4 * kRegsMma + 16 * kRegsEpi <= 24 * 80,
+              "register pool of the CTA (768 x 80)");
+constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-key window (8)
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
 constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
@@ -132,8 +135,11 @@ __device__ __forceinline__ void insert8(const int* k, int& m1, int& m2) {
 // Running state of one epilogue thread (one query row, half of the columns).
 struct RowTop2 {
   int g1v, g1i, g2v, g2i;   // best / second best of the finished windows: value = |t|^2 - 2 q.t
-  int m1, m2;               // top-2 of the current 512-column window as packed keys
-  int thr;                  // a group matters iff 2 max(q.t) - min|t|^2 > thr; thr = -second best
+  int m1, m2;               // top-2 of the current 1024-column window as packed keys
+  int bv;                   // bound: a group matters iff its smallest possible value
+                            // min|t|^2 - 2 max(q.t) is below bv = min(value of m2, second best
+                            // of the finished windows); equal values of later columns lose on
+                            // the index, so the comparison is strict
 };
 
 __device__ __forceinline__ bool lex_lt(int v, int i, int gv, int gi) {
@@ -151,7 +157,7 @@ __device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
   s.g1i = b1 ? i : s.g1i;
 }
 
-// exact keys of the 8 columns of group j (column keys from the shared-memory ring) -> (m1, m2)
+// exact keys of the 8 columns of a group (column keys from the shared-memory ring) -> (m1, m2)
 __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr, RowTop2& s) {
   const int4 c0 = lds_v4(ck_addr), c1 = lds_v4(ck_addr + 16);
   int k[8];
@@ -162,52 +168,23 @@ __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr
   insert8(k, s.m1, s.m2);
 }
 
-// Top-2 update with the thread's 64 columns of one tile (two 32-column chunks);
-// ck_addr = shared address of their keys.
-//   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
-//   kMode 1: only groups whose raw maximum beats the bound of some row of the warp.  All
-//            eight 3-input-max trees and votes are issued before any insert, so they overlap.
-template <int kMode>
-__device__ __forceinline__ void tile_update(const uint32_t (&r0)[32], const uint32_t (&r1)[32],
-                                            uint32_t ck_addr, uint32_t gm_addr, RowTop2& s) {
-  if constexpr (kMode == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) group_insert(&r0[8 * j], ck_addr + 32 * j, s);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) group_insert(&r1[8 * j], ck_addr + 128 + 32 * j, s);
-  } else {
-    bool h[8];
-    const int4 n0 = lds_v4(gm_addr), n1 = lds_v4(gm_addr + 16);
-    const int n8[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint32_t* r = j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)];
-      const int a = __vimax3_s32(r[0], r[1], r[2]);
-      const int b = __vimax3_s32(r[3], r[4], r[5]);
-      const int gm = max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
-      h[j] = __any_sync(0xffffffffu, gm * 2 - n8[j] > s.thr);
-    }
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (h[j]) {
-        group_insert(j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)], ck_addr + 32 * j, s);
-        any = true;
-      }
-    }
-    if (any) {
-      // the window's second best also bounds what can still enter (values, not keys)
-      const int w2 = s.m2 >> kColBits;
-      if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
-    }
-  }
+// largest raw dot product of a group of 8 accumulators: 3-input-max tree, 0.5 op per element
+__device__ __forceinline__ int group_max(const uint32_t* r) {
+  const int a = __vimax3_s32(r[0], r[1], r[2]);
+  const int b = __vimax3_s32(r[3], r[4], r[5]);
+  return max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
 }
 
-// Same for one 32-column chunk (4 groups); used by the software-pipelined loop, where the
-// next chunk's tcgen05.ld is in flight while this one is processed.
+// Top-2 update with one 32-column chunk (4 groups) of a tile; ck_addr / gm_addr = shared
+// addresses of the chunk's column keys and shifted group minima.
+//   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
+//   kMode 1: only groups whose smallest possible value beats the bound of some row of the
+//            warp: per group one IMAD, one compare and one vote on top of the max tree.
+//            neg2 = -2 in a register ptxas cannot see through, so that the multiply-add stays
+//            an IMAD on the FMA pipe instead of an IADD3 on the (limiting) ALU pipe.
 template <int kMode>
 __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
-                                             uint32_t gm_addr, RowTop2& s) {
+                                             uint32_t gm_addr, int neg2, RowTop2& s) {
   if constexpr (kMode == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
@@ -216,21 +193,26 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
     const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
     bool h[4];
 #pragma unroll
+    for (int j = 0; j < 4; ++j)
+      h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int a = __vimax3_s32(r[8 * j + 0], r[8 * j + 1], r[8 * j + 2]);
-      const int b = __vimax3_s32(r[8 * j + 3], r[8 * j + 4], r[8 * j + 5]);
-      const int gm = max(__vimax3_s32(a, b, r[8 * j + 6]), static_cast<int>(r[8 * j + 7]));
-      h[j] = __any_sync(0xffffffffu, gm * 2 - n8[j] > s.thr);
-    }
-    if (h[0]) group_insert(&r[0], ck_addr, s);
-    if (h[1]) group_insert(&r[8], ck_addr + 32, s);
-    if (h[2]) group_insert(&r[16], ck_addr + 64, s);
-    if (h[3]) group_insert(&r[24], ck_addr + 96, s);
-    if (h[0] | h[1] | h[2] | h[3]) {
-      const int w2 = s.m2 >> kColBits;
-      if (w2 < (1 << 22)) s.thr = max(s.thr, -w2);
+      if (h[j]) {
+        group_insert(&r[8 * j], ck_addr + 32 * j, s);
+        s.bv = min(s.bv, s.m2 >> kColBits);
+      }
     }
   }
+}
+
+// Close a packed-key window that started at train column `base`: merge its top-2 into the
+// (value, index) pairs and restart the window.
+__device__ __forceinline__ void close_window(RowTop2& s, int base) {
+  constexpr int kMask = (1 << kColBits) - 1;
+  insert_vi(s, s.m1 >> kColBits, base + (s.m1 & kMask));
+  insert_vi(s, s.m2 >> kColBits, base + (s.m2 & kMask));
+  s.m1 = INT32_MAX;
+  s.m2 = INT32_MAX;
 }
 
 template <int kMode>
@@ -299,8 +281,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
   // per MMA with `if (lane == 0)`).  768 threads leave 80 registers per thread; the control
   // warpgroups hand part of their share to the epilogue warpgroups (setmaxnreg at the top of
   // each role branch, so that ptxas allocates per branch).
-  if (warp < kFirstEpiWarp) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
+  if (warp < kFirstMmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProd));
     if (warp == 0) {
       // ===================================================== TMA producer
       uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0, tile_seq = 0;
@@ -356,7 +338,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           }
         }
       }
-    } else if (warp >= kFirstMmaWarp) {
+    }
+  } else if (warp < kFirstEpiWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+    {
       // ===================================================== MMA issuers: (half mh, parity mp)
       const uint32_t mh = (warp - kFirstMmaWarp) & 1, mp = (warp - kFirstMmaWarp) >> 1;
       constexpr uint32_t idesc = make_idesc_u8(kHalfM, kTileN);
@@ -403,27 +388,34 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     const int chalf = (e >> 2) & 1;                // which 64-column half of every tile
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row_in_blk = half * kHalfM + quarter * 32 + lane;
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                            half * kTileN + chalf * kColsPerThread;
+    // Loop invariants that ptxas would otherwise re-derive from %tid in front of every use
+    // (8 ALU instructions each time): pin them in registers.
+    uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * kTileN +
+                      chalf * kColsPerThread;
+    uint32_t bar_tf = bar_t_full(0, half), bar_te = bar_t_empty(0, half);   // + 16 * buffer
+    uint32_t ck_base = sCk + chalf * (kColsPerThread * 4);
+    uint32_t gm_base = sGm + chalf * (kColsPerThread / 8 * 4);
+    int neg2 = -2;
+    asm volatile("" : "+r"(t_addr), "+r"(bar_tf), "+r"(bar_te), "+r"(ck_base), "+r"(gm_base),
+                 "+r"(neg2));
     const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
     const uint32_t share_own = smem_base + kOffShare + row_in_blk * 16 + chalf * 8;
     const uint32_t share_other = smem_base + kOffShare + row_in_blk * 16 + (chalf ^ 1) * 8;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
     uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
-      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN};
-      int ntiles = 1, rows_valid = 0, norm_row = 0, nt_min = 0;
+      RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
+      int ntiles = 1, rows_valid = 0, norm_row = 0;
       int64_t knn_row = 0;
       if constexpr (kMode <= 1) {
         // ---- software-pipelined sweep: a tile is two 32-column chunks per thread; the
         // tcgen05.ld of the next chunk is in flight while the current one is processed, so
         // the TMEM read latency is off the warp's per-tile instruction chain
-        mbar_wait(bar_t_full(buf, half), bphase);
+        mbar_wait(bar_tf + 16 * buf, bphase);
         tc_fence_after();
         ntiles = info[abuf].ntiles;
         rows_valid = info[abuf].rows_valid;
         norm_row = info[abuf].norm_row;
-        nt_min = info[abuf].nt_min;
         knn_row = info[abuf].knn_row;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_empty(abuf));
@@ -432,62 +424,55 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         tmem_ld_x32(t_addr + buf * (2 * kTileN), ra);
         tmem_ld_wait();
         for (int t = 0; t < ntiles; ++t) {
-          const uint32_t ta = t_addr + buf * (2 * kTileN);
-          tmem_ld_x32(ta + 32, rb);                       // chunk 1 in flight
+          tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);    // chunk 1 in flight
           const uint32_t slot = tile_seq % kCkSlots;
-          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
-          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
-          chunk_update<kMode>(ra, ck_addr, gm_addr, st);
+          const uint32_t ck_addr = ck_base + slot * kCkBytes;
+          const uint32_t gm_addr = gm_base + slot * kGmBytes;
+          chunk_update<kMode>(ra, ck_addr, gm_addr, neg2, st);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));   // tile t is out of TMEM
+          if (lane == 0) mbar_arrive(bar_te + 16 * buf);        // tile t is out of TMEM
           const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
           if (t + 1 < ntiles) {
-            mbar_wait(bar_t_full(nbuf, half), nphase);
+            mbar_wait(bar_tf + 16 * nbuf, nphase);
             tc_fence_after();
             tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1 in flight
           }
-          chunk_update<kMode>(rb, ck_addr + 128, gm_addr + 16, st);
+          chunk_update<kMode>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
           if (t + 1 < ntiles) tmem_ld_wait();
-          if ((t & 3) == 3 || t == ntiles - 1) {
-            // close the 512-column window: merge its packed top-2 into the (value, index)
-            // pairs, then tighten the bound, also with the row partner's second best
-            const int base = (t & ~3) * kTileN;
-            insert_vi(st, st.m1 >> kColBits, base + (st.m1 & ((1 << kColBits) - 1)));
-            insert_vi(st, st.m2 >> kColBits, base + (st.m2 & ((1 << kColBits) - 1)));
-            st.m1 = INT32_MAX;
-            st.m2 = INT32_MAX;
+          if ((t & (kWinTiles - 1)) == kWinTiles - 1 || t == ntiles - 1) {
+            // close the 1024-column window, then tighten the bound, also with the row
+            // partner's second best (ties with the partner's columns go by index: + 1)
+            close_window(st, (t & ~(kWinTiles - 1)) * kTileN);
             int bound = st.g2v;
             if (kMode == 1) {
               sts_v2(share_own, item, st.g2v);
               const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
-              if (o.x == item && o.y < (1 << 22)) bound = min(bound, o.y + 1);
+              if (o.x == item && o.y < (1 << 21)) bound = min(bound, o.y + 1);
             }
-            st.thr = bound < (1 << 22) ? -bound : INT32_MIN;
+            st.bv = bound;
           }
           ++tile_seq;
           buf = nbuf;
           bphase = nphase;
         }
-      } else
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(bar_t_full(buf, half), bphase);
-        tc_fence_after();
-        if (t == 0) {
-          ntiles = info[abuf].ntiles;
-          rows_valid = info[abuf].rows_valid;
-          norm_row = info[abuf].norm_row;
-          nt_min = info[abuf].nt_min;
-          knn_row = info[abuf].knn_row;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a_empty(abuf));
-          abuf ^= 1;
-        }
-        const uint32_t ta = t_addr + buf * (2 * kTileN);
-        if constexpr (kMode >= 2) {
-          // timing experiments only (results are garbage):
-          // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
+      } else {
+        // ---- timing experiments only (results are garbage):
+        // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(bar_tf + 16 * buf, bphase);
+          tc_fence_after();
+          if (t == 0) {
+            ntiles = info[abuf].ntiles;
+            rows_valid = info[abuf].rows_valid;
+            norm_row = info[abuf].norm_row;
+            knn_row = info[abuf].knn_row;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_empty(abuf));
+            abuf ^= 1;
+          }
+          const uint32_t ta = t_addr + buf * (2 * kTileN);
           if constexpr (kMode == 2 || kMode == 4) {
             uint32_t r0[32], r1[32];
             tmem_ld_x32(ta, r0);
@@ -497,54 +482,20 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             if constexpr (kMode == 4) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int a = __vimax3_s32(r0[8 * j + 0], r0[8 * j + 1], r0[8 * j + 2]);
-                const int b = __vimax3_s32(r0[8 * j + 3], r0[8 * j + 4], r0[8 * j + 5]);
-                const int c = __vimax3_s32(r1[8 * j + 0], r1[8 * j + 1], r1[8 * j + 2]);
-                const int d = __vimax3_s32(r1[8 * j + 3], r1[8 * j + 4], r1[8 * j + 5]);
-                const int g0 = max(__vimax3_s32(a, b, r0[8 * j + 6]), static_cast<int>(r0[8 * j + 7]));
-                const int g1 = max(__vimax3_s32(c, d, r1[8 * j + 6]), static_cast<int>(r1[8 * j + 7]));
-                if (g0 > st.thr) { st.g1i = g0; ++st.g2v; }
-                if (g1 > st.thr) { st.g1i = g1; ++st.g2i; }
+                const int g0 = group_max(&r0[8 * j]), g1 = group_max(&r1[8 * j]);
+                if (g0 * neg2 < st.bv) { st.g1i = g0; ++st.g2v; }
+                if (g1 * neg2 < st.bv) { st.g1i = g1; ++st.g2i; }
               }
             }
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-        } else {
-          // pull this thread's 64 accumulators out of TMEM and hand the buffer back at once
-          uint32_t r0[32], r1[32];
-          tmem_ld_x32(ta, r0);
-          tmem_ld_x32(ta + 32, r1);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty(buf, half));
-          const uint32_t slot = tile_seq % kCkSlots;
-          const uint32_t ck_addr = sCk + slot * kCkBytes + chalf * (kColsPerThread * 4);
-          const uint32_t gm_addr = sGm + slot * kGmBytes + chalf * (kColsPerThread / 8 * 4);
-          tile_update<kMode>(r0, r1, ck_addr, gm_addr, st);
-          if ((t & 3) == 3 || t == ntiles - 1) {
-            // close the 512-column window: merge its packed top-2 into the (value, index)
-            // pairs, then tighten the bound, also with the row partner's second best
-            const int base = (t & ~3) * kTileN;
-            insert_vi(st, st.m1 >> kColBits, base + (st.m1 & ((1 << kColBits) - 1)));
-            insert_vi(st, st.m2 >> kColBits, base + (st.m2 & ((1 << kColBits) - 1)));
-            st.m1 = INT32_MAX;
-            st.m2 = INT32_MAX;
-            int bound = st.g2v;
-            if (kMode == 1) {
-              sts_v2(share_own, item, st.g2v);
-              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
-              if (o.x == item && o.y < (1 << 22)) bound = min(bound, o.y + 1);
-            }
-            st.thr = bound < (1 << 22) ? -bound : INT32_MIN;
+          if (lane == 0) mbar_arrive(bar_te + 16 * buf);
+          ++tile_seq;
+          if (++buf == kAccBufs) {
+            buf = 0;
+            bphase ^= 1;
           }
-        }
-        ++tile_seq;
-        if (++buf == kAccBufs) {
-          buf = 0;
-          bphase ^= 1;
         }
       }
       // merge the two column halves of the row: the upper half hands its top-2 over

@@ -7,10 +7,12 @@ namespace sfm {
 constexpr int kDim = 128;          // SIFT descriptor length in bytes (u8)
 constexpr int kTileM = 256;        // query rows per work item (two 128-lane TMEM halves)
 constexpr int kTileN = 128;        // train rows per B tile (TMEM columns per half)
-constexpr int kColBits = 9;        // packed key = (|t|^2 - 2 q.t) << 9 | (train row & 511): a
-                                   // key window is 4 train tiles; |value| < 2^21 keeps it in int32
+constexpr int kColBits = 10;       // packed key = (|t|^2 - 2 q.t) << 10 | (train row & 1023): a
+                                   // key window is 8 train tiles; |value| < 2^21 keeps it in int32
 constexpr int kRowPad = 256;       // every image is padded to a multiple of this many rows
-constexpr int kNormPad = 0x3FFFFF; // norm^2 sentinel of padding rows (never selected; << 9 fits)
+constexpr int kNormPad = 0x1FFFFF; // norm^2 sentinel of padding rows: >= every real value |t|^2 - 2 q.t
+                                   // (real norms <= 2^21 - 1) and behind them in index order, so a
+                                   // padding row is never selected when nt >= 2; << kColBits fits
 
 // One image pair of sfm_match_pairs.
 struct PairDesc {
