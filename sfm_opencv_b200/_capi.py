@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsfm_b200.so")
+# SFM_B200_LIB: development override used by tools/variants.py to time kernel build variants
+LIB_PATH = os.environ.get("SFM_B200_LIB") or os.path.join(_HERE, "libsfm_b200.so")
 
 SFM_OK = 0
 SFM_E_INVALID = -1

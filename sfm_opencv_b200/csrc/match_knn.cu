@@ -85,8 +85,8 @@ constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
 constexpr uint32_t kOffGm = kOffCk + kCkSlots * kCkBytes;
 constexpr uint32_t kOffInfo = kOffGm + kCkSlots * kGmBytes;
 constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
-constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int2
-constexpr uint32_t kOffBar = kOffShare + kTileM * 16;
+constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int4
+constexpr uint32_t kOffBar = kOffShare + kTileM * 32;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kKnnSmemBytes = kOffTmemPtr + 16 + 1024;   // + alignment slack
@@ -265,7 +265,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     fence_mbar_init();
   }
   if (threadIdx.x < kTileM)    // (item tag, second-best value) slots of the row-sharing threads
-    sts_v4(smem_base + kOffShare + threadIdx.x * 16, 0xffffffffu, 0, 0xffffffffu, 0);
+    for (int h = 0; h < 2; ++h)
+      sts_v4(smem_base + kOffShare + threadIdx.x * 32 + h * 16, 0xffffffffu, 0, 0, 0);
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -399,8 +400,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     asm volatile("" : "+r"(t_addr), "+r"(bar_tf), "+r"(bar_te), "+r"(ck_base), "+r"(gm_base),
                  "+r"(neg2));
     const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
-    const uint32_t share_own = smem_base + kOffShare + row_in_blk * 16 + chalf * 8;
-    const uint32_t share_other = smem_base + kOffShare + row_in_blk * 16 + (chalf ^ 1) * 8;
+    const uint32_t share_own = smem_base + kOffShare + row_in_blk * 32 + chalf * 16;
+    const uint32_t share_other = smem_base + kOffShare + row_in_blk * 32 + (chalf ^ 1) * 16;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
     uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
     for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
@@ -443,13 +444,18 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           if (t + 1 < ntiles) tmem_ld_wait();
           if ((t & (kWinTiles - 1)) == kWinTiles - 1 || t == ntiles - 1) {
             // close the 1024-column window, then tighten the bound, also with the row
-            // partner's second best (ties with the partner's columns go by index: + 1)
+            // partner's top-2 (ties with the partner's columns go by index: + 1)
             close_window(st, (t & ~(kWinTiles - 1)) * kTileN);
             int bound = st.g2v;
             if (kMode == 1) {
-              sts_v2(share_own, item, st.g2v);
-              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
-              if (o.x == item && o.y < (1 << 21)) bound = min(bound, o.y + 1);
+              // the row's second best over BOTH column halves bounds what can still enter:
+              // second smallest of {own best, own second, partner's best, partner's second}
+              sts_v4(share_own, item, st.g1v, st.g2v, 0);
+              const int4 o = lds_v4(share_other);   // any earlier value of this item is valid
+              if (o.x == item) {
+                const int joint = min(max(st.g1v, o.y), o.z);
+                if (joint < (1 << 21)) bound = min(bound, joint + 1);
+              }
             }
             st.bv = bound;
           }
