@@ -49,7 +49,7 @@ enum {
   SFM_E_INVALID = -1,        /* null pointer, negative size, bad index ...        */
   SFM_E_NO_DEVICE = -2,      /* no CUDA device / not compute capability 10.x      */
   SFM_E_CUDA = -3,           /* a CUDA runtime / driver call failed               */
-  SFM_E_DIM = -4,            /* descriptor dimension is not 128                   */
+  SFM_E_DIM = -4,            /* descriptor dimension is not 128 (binary: not 1..64) */
   SFM_E_NOT_INTEGRAL = -5,   /* float descriptor holds a non-integer value        */
   SFM_E_RANGE = -6,          /* descriptor value outside 0..255, or row norm^2
                                 so large that float sqrt is no longer injective   */
@@ -107,6 +107,16 @@ SFM_API int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* 
 /* Same, for callers that already hold uint8 descriptors (4x less PCIe traffic). */
 SFM_API int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
                               const int32_t* n_desc, int dim);
+
+/* Binary descriptors for the reference's LIVE configuration: AKAZE descriptors (61 bytes,
+ * CV_8U) matched with BFMatcher(NORM_HAMMING2) (NViewReconstuct.cpp:797, :875-877).
+ * desc_u8[i] is a row-major n_desc[i] x bytes uint8 matrix, 1 <= bytes <= 64.  After this
+ * upload sfm_match_pairs / sfm_match_pairs_resident compute cv::NORM_HAMMING2 distances
+ * (number of differing 2-bit cells; sfm_match_t::distance holds that integer as a float,
+ * as cv::DMatch does) with the same (distance, lower train index) order and the same two
+ * filter passes.  Replaces any previously uploaded bank. */
+SFM_API int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
+                               const int32_t* n_desc, int bytes);
 
 /* For every pair p: knnMatch(desc[pair_q[p]], desc[pair_t[p]], k=2) with NORM_L2,
  * then the reference's two filter passes (NViewReconstuct.cpp:880-908):

@@ -80,11 +80,26 @@ class Context:
         return int(self._lib.sfm_launch_count(self._h))
 
     # ------------------------------------------------------------------ matching
-    def upload_descriptors(self, descriptor_for_all):
-        """descriptor_for_all: list of [n_i,128] arrays, float32 (as cv::SIFT gives) or uint8."""
+    def upload_descriptors(self, descriptor_for_all, norm: str = "l2"):
+        """descriptor_for_all: list of [n_i,128] arrays, float32 (as cv::SIFT gives) or uint8.
+        norm="hamming2": list of [n_i,B<=64] uint8 binary descriptors (AKAZE: B=61), matched
+        with cv::NORM_HAMMING2 as the live reference does (NViewReconstuct.cpp:797,876)."""
         descs = [np.ascontiguousarray(d) for d in descriptor_for_all]
         if not descs:
             raise SfmError(_capi.SFM_E_INVALID, "empty image list")
+        if norm == "hamming2":
+            if any(d.dtype != np.uint8 for d in descs):
+                raise SfmError(_capi.SFM_E_INVALID, "binary descriptors must be uint8")
+            widths = {d.shape[1] for d in descs if d.ndim == 2}
+            width = widths.pop() if len(widths) == 1 else -1
+            n = np.array([d.shape[0] for d in descs], np.int32)
+            ptrs = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs])
+            self._check(self._lib.sfm_upload_descriptors_bin(self._h, len(descs), ptrs,
+                                                             _ptr(n, C.c_int32), width))
+            self.n_desc = [int(x) for x in n]
+            return
+        if norm != "l2":
+            raise SfmError(_capi.SFM_E_INVALID, "norm must be 'l2' or 'hamming2'")
         is_u8 = all(d.dtype == np.uint8 for d in descs)
         if not is_u8:
             descs = [np.ascontiguousarray(d, dtype=np.float32) for d in descs]
@@ -235,16 +250,17 @@ class Context:
 
 # ---------------------------------------------------------------------- reference-shaped API
 
-def match_features(ctx: Context, query, train, **kw):
-    """match_features(query, train, matches), NViewReconstuct.cpp:873: returns the DMatch array."""
-    ctx.upload_descriptors([query, train])
+def match_features(ctx: Context, query, train, norm: str = "l2", **kw):
+    """match_features(query, train, matches), NViewReconstuct.cpp:873: returns the DMatch array.
+    norm="hamming2" is the live file's BFMatcher(NORM_HAMMING2) (:876), "l2" the SIFT form."""
+    ctx.upload_descriptors([query, train], norm=norm)
     m, _, _ = ctx.match_pairs([(0, 1)], **kw)
     return m[0]
 
 
-def match_features_for_all(ctx: Context, descriptor_for_all, **kw):
+def match_features_for_all(ctx: Context, descriptor_for_all, norm: str = "l2", **kw):
     """match_features_for_all, NViewReconstuct.cpp:850-871: consecutive pairs (i, i+1)."""
-    ctx.upload_descriptors(descriptor_for_all)
+    ctx.upload_descriptors(descriptor_for_all, norm=norm)
     pairs = [(i, i + 1) for i in range(len(descriptor_for_all) - 1)]
     m, _, _ = ctx.match_pairs(pairs, **kw)
     return m

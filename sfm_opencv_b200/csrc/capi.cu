@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,12 @@ cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pa
                                 const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
                                 cudaStream_t s);
 cudaError_t launch_knn_to_float(const Knn2* knn, int64_t n, sfm_knn2_t* out, cudaStream_t s);
+// match_hamming.cu
+cudaError_t launch_bin_pack(const uint8_t* src, int n, int bytes, int row0, uint8_t* bank,
+                            cudaStream_t s);
+cudaError_t launch_hamming2_knn(const uint8_t* bank, const PairDesc* pairs, const int2* items,
+                                int n_items, int n_splits, int2* partial, int64_t n_rows,
+                                Knn2* knn, cudaStream_t s);
 // geometry.cu
 int geometry_grid(int64_t n, int n_sms);
 cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,
@@ -94,6 +101,8 @@ struct sfm_ctx {
   std::vector<int2> h_items;                   // reused host staging of the work-item table
   int64_t bank_rows = 0;
   bool bank_ready = false;
+  bool bank_binary = false;   // false: u8 x 128 (NORM_L2); true: 64-byte rows (NORM_HAMMING2)
+  DevBuf partial;             // NORM_HAMMING2: per-split top-2 of every query row
   CUtensorMap tmap;   // u8 bank, box = 128 rows x 128 bytes, 128-byte swizzle
 
   // matching scratch
@@ -195,7 +204,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
-                    &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -318,6 +327,7 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
                 "descriptor row norm^2 >= 2^21: float sqrt no longer injective on the distances");
   int rc = make_tmap(ctx, &ctx->tmap, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
   if (rc) return rc;
+  ctx->bank_binary = false;
   ctx->bank_ready = true;
   return SFM_OK;
 }
@@ -332,6 +342,52 @@ int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* des
                               const int32_t* n_desc, int dim) {
   return upload_common(ctx, n_img, reinterpret_cast<const void* const*>(desc_u8), n_desc, dim,
                        false);
+}
+
+// Binary descriptors for NORM_HAMMING2 (the live AKAZE path, NViewReconstuct.cpp:797,876).
+int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
+                               const int32_t* n_desc, int bytes) {
+  constexpr int kBinRowPad = 128, kBinRowBytes = 64;
+  if (!ctx) return SFM_E_INVALID;
+  if (n_img <= 0 || !desc_u8 || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
+  if (bytes <= 0 || bytes > kBinRowBytes)
+    return fail(ctx, SFM_E_DIM, "binary descriptors must be 1..64 bytes (AKAZE: 61)");
+  CK(cudaSetDevice(ctx->device));
+  ctx->bank_ready = false;
+  ctx->last_valid = false;
+  ctx->img_n.assign(n_desc, n_desc + n_img);
+  ctx->img_row0.resize(n_img);
+  ctx->img_min_norm.assign(n_img, 0);
+  int64_t rows = 0;
+  int32_t max_n = 0;
+  for (int i = 0; i < n_img; ++i) {
+    if (n_desc[i] < 0 || (n_desc[i] > 0 && !desc_u8[i]))
+      return fail(ctx, SFM_E_INVALID, "negative count or null descriptor pointer");
+    if (n_desc[i] >= (1 << 20))
+      return fail(ctx, SFM_E_INVALID, "more than 2^20 binary descriptors in one image");
+    ctx->img_row0[i] = static_cast<int32_t>(rows);
+    rows += (static_cast<int64_t>(n_desc[i]) + kBinRowPad - 1) / kBinRowPad * kBinRowPad;
+    if (n_desc[i] > max_n) max_n = n_desc[i];
+    if (rows >= (1ll << 31) / kBinRowBytes) return fail(ctx, SFM_E_INVALID, "descriptor bank too large");
+  }
+  if (rows == 0) rows = kBinRowPad;
+  ctx->bank_rows = rows;
+  CK(ctx->desc.ensure(static_cast<size_t>(rows) * kBinRowBytes));
+  const size_t img_bytes = (static_cast<size_t>(max_n) * bytes + 255) / 256 * 256;
+  CK(ctx->stage.ensure(2 * img_bytes + 512));
+  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kBinRowBytes, ctx->stream));
+  for (int i = 0; i < n_img; ++i) {
+    uint8_t* st = ctx->stage.as<uint8_t>() + (i & 1) * img_bytes;
+    const size_t nb = static_cast<size_t>(n_desc[i]) * bytes;
+    if (!nb) continue;
+    CK(cudaMemcpyAsync(st, desc_u8[i], nb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_bin_pack(st, n_desc[i], bytes, ctx->img_row0[i], ctx->desc.as<uint8_t>(), ctx->stream));
+    ctx->launches += 1;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->bank_binary = true;
+  ctx->bank_ready = true;
+  return SFM_OK;
 }
 
 // ----------------------------------------------------------------------------- matching
@@ -365,7 +421,8 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     pd.pad = 0;
     pd.knn_off = rows;
     rows += pd.nq;
-    const int mb = (pd.nq + kTileM - 1) / kTileM;
+    const int qblock = ctx->bank_binary ? 128 : kTileM;   // query rows per work item
+    const int mb = (pd.nq + qblock - 1) / qblock;
     for (int m = 0; m < mb; ++m) items.push_back(make_int2(p, m));
     if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many query blocks");
   }
@@ -384,10 +441,24 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(int2) * n_items, cudaMemcpyHostToDevice,
                        ctx->stream));
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
-                 ctx->norm.as<int32_t>(),
-                 ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(), static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
-  if (n_items > 0) ctx->launches += 1;
+  if (ctx->bank_binary) {
+    // NORM_HAMMING2: split every train image over enough blocks to fill the device
+    int n_splits = 1;
+    if (n_items > 0) {
+      const int64_t want = 8ll * ctx->n_sms;
+      n_splits = static_cast<int>(std::min<int64_t>(16, std::max<int64_t>(1, (want + n_items - 1) / n_items)));
+    }
+    CK(ctx->partial.ensure(sizeof(int2) * static_cast<size_t>(rows + 1) * n_splits));
+    CK(launch_hamming2_knn(ctx->desc.as<uint8_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
+                           static_cast<int>(n_items), n_splits, ctx->partial.as<int2>(), rows,
+                           ctx->knn.as<Knn2>(), ctx->stream));
+    if (n_items > 0) ctx->launches += 2;
+  } else {
+    CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
+                   ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
+                   static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+    if (n_items > 0) ctx->launches += 1;
+  }
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
                    gate_mult, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),

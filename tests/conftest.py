@@ -27,6 +27,6 @@ def ctx():
 def golden():
     import numpy as np
 
-    def load(name):
-        return np.load(os.path.join(GOLDEN, f"{name}_sift.npz"))
+    def load(name, kind="sift"):
+        return np.load(os.path.join(GOLDEN, f"{name}_{kind}.npz"))
     return load

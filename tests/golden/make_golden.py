@@ -39,6 +39,43 @@ def sift_dataset(name: str):
     return files, descs, kps
 
 
+def akaze_dataset(name: str):
+    """The LIVE path's features: AKAZE_create() + detect/compute (NViewReconstuct.cpp:797-814)."""
+    files = sorted(glob.glob(os.path.join(REF, name, "*.[jJ][pP][gG]")))
+    ak = cv2.AKAZE_create()
+    descs, kps = [], []
+    for f in files:
+        img = cv2.imread(f)
+        kp = ak.detect(img, None)
+        kp, d = ak.compute(img, kp)
+        descs.append(np.ascontiguousarray(d, np.uint8))
+        kps.append(np.array([k.pt for k in kp], np.float32))
+        print(name, "akaze", os.path.basename(f), d.shape, flush=True)
+    return files, descs, kps
+
+
+def main_akaze():
+    """desktop / AKAZE / NORM_HAMMING2: the configuration that produced the reference's bundled
+    Viewer/structure.yml (expected match counts 2186 / 1063 / 230 / 553)."""
+    name = "desktop"
+    files, descs, kps = akaze_dataset(name)
+    out = {"n_img": np.int32(len(descs))}
+    for i, (d, k) in enumerate(zip(descs, kps)):
+        out[f"desc_{i}"] = d
+        out[f"kp_{i}"] = k
+    for i in range(len(descs) - 1):
+        dist, idx = M.knn2_cv_hamming2(descs[i], descs[i + 1])   # the reference's library call
+        m, d0, md = M.filter_matches(dist, idx)
+        out[f"knn_dist_{i}"] = dist
+        out[f"knn_idx_{i}"] = idx
+        out[f"match_{i}"] = m
+        out[f"match_dist_{i}"] = d0
+        out[f"min_dist_{i}"] = np.float32(md)
+        print(name, "akaze pair", i, "matches", len(m), "min_dist", md, "tie rows",
+              int((dist[:, 0] == dist[:, 1]).sum()), flush=True)
+    np.savez_compressed(os.path.join(OUT, f"{name}_akaze.npz"), **out)
+
+
 def main():
     for name in ("crazyhorse", "desktop"):
         files, descs, kps = sift_dataset(name)
@@ -62,4 +99,6 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--akaze-only" not in sys.argv:
+        main()
+    main_akaze()
