@@ -175,6 +175,24 @@ SFM_API int sfm_reproject_residuals(sfm_ctx* ctx, const double intr[4], const do
                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
                             double huber_delta, double* resid, double* huber_cost);
 
+/* ---- output files: save_structure() / write_ply_binary() ---------------------------- */
+
+/* Writes the file save_structure() writes (NViewReconstuct.cpp:186-227) byte for byte as
+ * cv::FileStorage (YAML 1.0) would: "Camera Count", "Point Count", "Rotations" (n_cam 3x3
+ * CV_64F matrices, row-major), "Motions" (n_cam 3x1), "Points" (n_pts Point3d) and "Colors"
+ * (n_colors Vec3b, stored b,g,r as the reference holds them).  Host-only (no device). */
+SFM_API int sfm_save_structure(const char* file_name, int n_cam, const double* rotations,
+                       const double* motions, int64_t n_pts, const double* structure,
+                       int64_t n_colors, const uint8_t* colors);
+
+/* write_ply_binary() (NViewReconstuct.cpp:229-294): binary little-endian PLY, 27 bytes per
+ * vertex (x y z nx ny nz as float, r g b as uchar); xyz_normal is [n][6], rgb [n][3];
+ * vertices holding a NaN are skipped and not counted, as in the reference.  crlf != 0 writes
+ * the header lines with "\r\n", which is what the reference's text-mode stream produces on
+ * its platform (and what the bundled Viewer/structure_ba.ply holds). Host-only. */
+SFM_API int sfm_write_ply_binary(const char* path, int64_t n, const float* xyz_normal,
+                         const uint8_t* rgb, int crlf);
+
 /* ---- device-resident benchmarking hooks (inputs already in HBM) --------------------- */
 
 /* Stages the inputs of sfm_triangulate_batch / sfm_reproject_residuals on the device

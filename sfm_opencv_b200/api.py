@@ -302,6 +302,41 @@ def bundle_adjustment_residuals(ctx: Context, intrinsic, extrinsics, inds_2d_to_
     return r, cost, float(np.sqrt(cost / n))
 
 
+def save_structure(file_name, rotations, motions, structure, colors):
+    """save_structure(file_name, rotations, motions, structure, colors), NViewReconstuct.cpp:
+    186-227: the cv::FileStorage YAML the viewer loads, written by the library's own emitter
+    (byte-identical to OpenCV's).  rotations: n x 3x3, motions: n x 3x1, structure: [N,3]
+    float64, colors: [M,3] uint8 in the reference's b,g,r order."""
+    lib = _capi.load()
+    R = np.ascontiguousarray(np.asarray(rotations, np.float64).reshape(-1, 9))
+    T = np.ascontiguousarray(np.asarray(motions, np.float64).reshape(-1, 3))
+    if R.shape[0] != T.shape[0]:
+        raise SfmError(_capi.SFM_E_INVALID, "rotations and motions differ in length")
+    X = np.ascontiguousarray(np.asarray(structure, np.float64).reshape(-1, 3))
+    c = np.ascontiguousarray(np.asarray(colors, np.uint8).reshape(-1, 3))
+    rc = lib.sfm_save_structure(str(file_name).encode(), R.shape[0], _ptr(R, C.c_double),
+                                _ptr(T, C.c_double), X.shape[0], _ptr(X, C.c_double),
+                                c.shape[0], _ptr(c, C.c_uint8))
+    if rc:
+        raise SfmError(rc, f"cannot write {file_name}")
+
+
+def write_ply_binary(path, xyz, normals, rgb, crlf: bool = True):
+    """write_ply_binary(path, points), NViewReconstuct.cpp:229-294: 27 bytes per vertex
+    (x y z nx ny nz float32, r g b uint8), NaN vertices skipped.  crlf=True gives the header
+    line ends the reference produces on its platform (bundled Viewer/structure_ba.ply)."""
+    lib = _capi.load()
+    v = np.ascontiguousarray(np.concatenate([np.asarray(xyz, np.float32).reshape(-1, 3),
+                                             np.asarray(normals, np.float32).reshape(-1, 3)], 1))
+    c = np.ascontiguousarray(np.asarray(rgb, np.uint8).reshape(-1, 3))
+    if c.shape[0] != v.shape[0]:
+        raise SfmError(_capi.SFM_E_INVALID, "points and colours differ in length")
+    rc = lib.sfm_write_ply_binary(str(path).encode(), v.shape[0], _ptr(v, C.c_float),
+                                  _ptr(c, C.c_uint8), int(crlf))
+    if rc:
+        raise SfmError(rc, f"cannot write {path}")
+
+
 def reconstruct(ctx: Context, K, R1, T1, R2, T2, p1, p2):
     """reconstruct(K,R1,T1,R2,T2,p1,p2,structure), NViewReconstuct.cpp:1117: returns structure
     [N,3] float64 (Point3d); raises on empty input where the reference returns -1."""
