@@ -161,6 +161,35 @@ SFM_API int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const 
 SFM_API int sfm_triangulate_batch(sfm_ctx* ctx, const float* P, const float* xy, int n_views,
                           int64_t n_pts, float* X4, double* xyz);
 
+/* ---- match list -> points -> structure without a host round trip ----------------------
+ *
+ * The reference turns a pair's match list into 3-D points on the host:
+ * get_matched_points (NViewReconstuct.cpp:989-1003), maskout_points (:943), the float32
+ * projection build and cv::triangulatePoints + de-homogenise in reconstruct() (:1117-1159).
+ * Here the match list of the last sfm_match_pairs call stays on the device and is consumed
+ * there. */
+
+/* Pixel coordinates of every image's keypoints (cv::KeyPoint::pt of key_points_for_all,
+ * :1366): kp_xy[i] is n_kp[i] x 2 float; n_kp[i] must equal the descriptor count. */
+SFM_API int sfm_upload_keypoints(sfm_ctx* ctx, int n_img, const float* const* kp_xy,
+                         const int32_t* n_kp);
+
+/* get_matched_points for pair `pair` (index into the last sfm_match_pairs call): out_p1[i] =
+ * kp[query][match.queryIdx], out_p2[i] = kp[train][match.trainIdx], optionally compacted by
+ * mask (nullable, one byte per match, kept when > 0, as maskout_points does).  n_points
+ * receives the number of points; SFM_E_CAPACITY when it exceeds cap. */
+SFM_API int sfm_get_matched_points(sfm_ctx* ctx, int pair, const uint8_t* mask, float* out_p1,
+                           float* out_p2, int64_t cap, int64_t* n_points);
+
+/* reconstruct(K, R1, T1, R2, T2, p1, p2, structure) on the (masked) matches of `pair`:
+ * device-side gather, P = float32(K) * float32([R|T]) (:1129-1143), DLT triangulation and
+ * float32 de-homogenise; structure is [n_points][3] double == std::vector<cv::Point3d>.
+ * K, R1, R2 are row-major 3x3, T1, T2 3-vectors (CV_64F in the reference).  No matches left
+ * is the reference's "[Err]: empty 2d points." (-1): SFM_E_INVALID. */
+SFM_API int sfm_reconstruct_pair(sfm_ctx* ctx, int pair, const double K[9], const double R1[9],
+                         const double T1[3], const double R2[9], const double T2[3],
+                         const uint8_t* mask, double* structure, int64_t cap, int64_t* n_points);
+
 /* ---- reprojection residuals: replaces ReprojectCost::operator() evaluation --------- */
 
 /* intr = {fx, fy, cx, cy} (:1464-1471); ext[c] = {angle-axis(3), t(3)} (:1478-1486);

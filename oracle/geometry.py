@@ -36,12 +36,15 @@ K_REFERENCE = np.array([[2826.561, 0.0, 1835.259],
 
 
 def build_projection(K, R, T) -> np.ndarray:
-    """P = float32(K) @ float32([R|T]) -- a float32 product, NViewReconstuct.cpp:1129-1143."""
+    """P = float32(K) * float32([R|T]), NViewReconstuct.cpp:1129-1143, with cv::gemm's
+    evaluation order (pinned against cv2.gemm in tests/test_oracle_geometry.py)."""
     RT = np.empty((3, 4), np.float32)
     RT[:, :3] = np.asarray(R, np.float64).astype(np.float32)
     RT[:, 3] = np.asarray(T, np.float64).reshape(3).astype(np.float32)
     fK = np.asarray(K, np.float64).astype(np.float32)
-    return (fK @ RT).astype(np.float32)
+    # cv::gemm's small-matrix path: ((a0*b0 + a1*b1) + a2*b2) in float32, no FMA
+    p = fK[:, :, None] * RT[None, :, :]                  # float32 products [r, k, c]
+    return ((p[:, 0, :] + p[:, 1, :]) + p[:, 2, :]).astype(np.float32)
 
 
 def dlt_matrix(P: np.ndarray, xy: np.ndarray) -> np.ndarray:

@@ -35,6 +35,9 @@ SYMBOLS = {
     "sfm_upload_descriptors": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_upload_descriptors_u8": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_upload_descriptors_bin": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
+    "sfm_upload_keypoints": (_i, [_vp, _i, C.POINTER(_vp), _pi]),
+    "sfm_get_matched_points": (_i, [_vp, _i, C.POINTER(C.c_uint8), _pf, _pf, _i64, _pi64]),
+    "sfm_reconstruct_pair": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, C.POINTER(C.c_uint8), _pd, _i64, _pi64]),
     "sfm_save_structure": (_i, [C.c_char_p, _i, _pd, _pd, _i64, _pd, _i64, C.POINTER(C.c_uint8)]),
     "sfm_write_ply_binary": (_i, [C.c_char_p, _i64, _pf, C.POINTER(C.c_uint8), _i]),
     "sfm_match_pairs": (_i, [_vp, _pi, _pi, _i, _d, _f, _f, _vp, _i64, _pi64, _vp, _pf]),

@@ -169,6 +169,43 @@ class Context:
                 r += self.n_desc[q]
         return matches, min_dist[:n_pairs], knn_list
 
+    # ------------------------------------------------------------------ matches -> structure
+    def upload_keypoints(self, key_points_for_all):
+        """key_points_for_all: per image an [n_i,2] float32 array of cv::KeyPoint::pt."""
+        kps = [np.ascontiguousarray(k, np.float32).reshape(-1, 2) for k in key_points_for_all]
+        n = np.array([k.shape[0] for k in kps], np.int32)
+        ptrs = (C.c_void_p * len(kps))(*[k.ctypes.data for k in kps])
+        self._check(self._lib.sfm_upload_keypoints(self._h, len(kps), ptrs, _ptr(n, C.c_int32)))
+
+    def _mask_arg(self, mask):
+        if mask is None:
+            return None, None
+        m = np.ascontiguousarray(np.asarray(mask).reshape(-1), np.uint8)
+        return m, _ptr(m, C.c_uint8)
+
+    def get_matched_points(self, pair: int, n_matches: int, mask=None):
+        """get_matched_points (+ maskout_points) for pair `pair` of the last match_pairs call,
+        gathered on the device.  Returns (p1 [n,2], p2 [n,2]) float32."""
+        m, pm = self._mask_arg(mask)
+        p1 = np.empty((max(n_matches, 1), 2), np.float32)
+        p2 = np.empty((max(n_matches, 1), 2), np.float32)
+        n = C.c_int64(0)
+        self._check(self._lib.sfm_get_matched_points(self._h, pair, pm, _ptr(p1, C.c_float),
+                                                     _ptr(p2, C.c_float), n_matches, C.byref(n)))
+        return p1[:n.value], p2[:n.value]
+
+    def reconstruct_pair(self, pair: int, n_matches: int, K, R1, T1, R2, T2, mask=None):
+        """reconstruct() over the (masked) matches of pair `pair` of the last match_pairs call
+        without bringing the match list to the host.  Returns structure [n,3] float64."""
+        m, pm = self._mask_arg(mask)
+        a = [np.ascontiguousarray(x, np.float64).reshape(-1) for x in (K, R1, T1, R2, T2)]
+        out = np.empty((max(n_matches, 1), 3), np.float64)
+        n = C.c_int64(0)
+        self._check(self._lib.sfm_reconstruct_pair(
+            self._h, pair, *[_ptr(x, C.c_double) for x in a], pm, _ptr(out, C.c_double), n_matches,
+            C.byref(n)))
+        return out[:n.value]
+
     def match_pairs_resident(self, pairs, ratio=RATIO, dist_floor=DIST_FLOOR,
                              gate_mult=GATE_MULT):
         """Device-resident timing hook: returns (total_matches, knn_kernel_ms, total_ms)."""
@@ -267,11 +304,15 @@ def match_features_for_all(ctx: Context, descriptor_for_all, norm: str = "l2", *
 
 
 def build_projection(K, R, T) -> np.ndarray:
-    """proj = fK * [R|T] as a float32 product, NViewReconstuct.cpp:1129-1143 (host glue)."""
+    """proj = fK * [R|T], NViewReconstuct.cpp:1129-1143 (host glue), evaluated as cv::gemm does
+    for CV_32F operands so that P is bit-identical to the reference's."""
     RT = np.empty((3, 4), np.float32)
     RT[:, :3] = np.asarray(R, np.float64).astype(np.float32)
     RT[:, 3] = np.asarray(T, np.float64).reshape(3).astype(np.float32)
-    return (np.asarray(K, np.float64).astype(np.float32) @ RT).astype(np.float32)
+    fK = np.asarray(K, np.float64).astype(np.float32)
+    # cv::gemm's small-matrix path: ((a0*b0 + a1*b1) + a2*b2) in float32, no FMA
+    p = fK[:, :, None] * RT[None, :, :]                  # float32 products [r, k, c]
+    return ((p[:, 0, :] + p[:, 1, :]) + p[:, 2, :]).astype(np.float32)
 
 
 def enumerate_observations(inds_2d_to_3d, keypoints_xy):

@@ -42,6 +42,9 @@ cudaError_t launch_hamming2_knn(const uint8_t* bank, const PairDesc* pairs, cons
 int geometry_grid(int64_t n, int n_sms);
 cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,
                                float* X4, double* xyz, int n_sms, cudaStream_t s);
+cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32_t* sel, int64_t n,
+                                         const float* kp_q, const float* kp_t, float* xy,
+                                         cudaStream_t s);
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
 cudaError_t launch_residuals(const double intr[4], const double* cam, const double* pts,
                              const int32_t* cam_idx, const int32_t* pt_idx, const float* obs_xy,
@@ -113,6 +116,12 @@ struct sfm_ctx {
   int last_n_pairs = 0;
   double last_ratio = 0.0;
   float last_floor = 0.f, last_mult = 0.f;
+  std::vector<int32_t> last_pair_q, last_pair_t;   // image ids of the last call's pairs
+  std::vector<int64_t> last_offsets;               // host copy of its CSR offsets
+  // keypoint bank (cv::KeyPoint::pt of every image) for the device-side match -> point gather
+  DevBuf kp, gsel;
+  std::vector<int64_t> kp_off;
+  bool kp_ready = false;
   // geometry scratch
   DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
 };
@@ -204,7 +213,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
-                    &ctx->partial, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->kp, &ctx->gsel, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -515,6 +524,9 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->last_total = offsets[n_pairs];
+  ctx->last_offsets.assign(offsets, offsets + n_pairs + 1);
+  ctx->last_pair_q.assign(pair_q, pair_q + n_pairs);
+  ctx->last_pair_t.assign(pair_t, pair_t + n_pairs);
   ctx->last_n_pairs = n_pairs;
   ctx->last_ratio = ratio;
   ctx->last_floor = dist_floor;
@@ -618,6 +630,138 @@ int sfm_triangulate_batch_timed(sfm_ctx* ctx, const float* P, const float* xy, i
                                 float* ms_per_launch) {
   if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
   return triangulate_common(ctx, P, xy, n_views, n_pts, X4, xyz, iters, ms_per_launch);
+}
+
+// ------------------------------------------------------------- match list -> 3-D structure
+int sfm_upload_keypoints(sfm_ctx* ctx, int n_img, const float* const* kp_xy, const int32_t* n_kp) {
+  if (!ctx) return SFM_E_INVALID;
+  if (n_img <= 0 || !kp_xy || !n_kp) return fail(ctx, SFM_E_INVALID, "null or empty image list");
+  CK(cudaSetDevice(ctx->device));
+  ctx->kp_ready = false;
+  ctx->kp_off.assign(n_img + 1, 0);
+  for (int i = 0; i < n_img; ++i) {
+    if (n_kp[i] < 0 || (n_kp[i] > 0 && !kp_xy[i]))
+      return fail(ctx, SFM_E_INVALID, "negative count or null keypoint pointer");
+    ctx->kp_off[i + 1] = ctx->kp_off[i] + n_kp[i];
+  }
+  CK(ctx->kp.ensure(8 * static_cast<size_t>(ctx->kp_off[n_img]) + 8));
+  for (int i = 0; i < n_img; ++i)
+    if (n_kp[i])
+      CK(cudaMemcpyAsync(ctx->kp.as<float>() + 2 * ctx->kp_off[i], kp_xy[i], 8 * static_cast<size_t>(n_kp[i]),
+                         cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->kp_ready = true;
+  return SFM_OK;
+}
+
+// proj = fK * [R|T] exactly as cv::gemm evaluates the reference's CV_32F MatExpr
+// (NViewReconstuct.cpp:1141-1143): every element is ((a0*b0 + a1*b1) + a2*b2) in float32, left
+// to right, separate multiplies and adds (no FMA) -- checked bit for bit against cv2.gemm.
+static void build_projection(const double K[9], const double R[9], const double T[3], float P[12]) {
+  float fK[9], RT[12];
+  for (int i = 0; i < 9; ++i) fK[i] = static_cast<float>(K[i]);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) RT[4 * r + c] = static_cast<float>(R[3 * r + c]);
+    RT[4 * r + 3] = static_cast<float>(T[r]);
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      volatile float p0 = fK[3 * r + 0] * RT[c];          // volatile: keeps the compiler from
+      volatile float p1 = fK[3 * r + 1] * RT[4 + c];      // contracting into fused multiply-adds
+      volatile float p2 = fK[3 * r + 2] * RT[8 + c];
+      volatile float s01 = p0 + p1;
+      P[4 * r + c] = s01 + p2;
+    }
+}
+
+// Stages the (masked) matches of `pair` as view-major points in ctx->gxy; returns their number.
+static int gather_pair(sfm_ctx* ctx, int pair, const uint8_t* mask, int64_t* n_out) {
+  if (!ctx->last_valid) return fail(ctx, SFM_E_INVALID, "no sfm_match_pairs result on the device");
+  if (!ctx->kp_ready) return fail(ctx, SFM_E_NOT_UPLOADED, "call sfm_upload_keypoints first");
+  if (pair < 0 || pair >= ctx->last_n_pairs) return fail(ctx, SFM_E_INVALID, "pair index out of range");
+  const int q = ctx->last_pair_q[pair], t = ctx->last_pair_t[pair];
+  const int n_img = static_cast<int>(ctx->kp_off.size()) - 1;
+  if (q >= n_img || t >= n_img || ctx->kp_off[q + 1] - ctx->kp_off[q] != ctx->img_n[q] ||
+      ctx->kp_off[t + 1] - ctx->kp_off[t] != ctx->img_n[t])
+    return fail(ctx, SFM_E_INVALID, "keypoint and descriptor counts of the pair's images differ");
+  const int64_t off = ctx->last_offsets[pair], n_all = ctx->last_offsets[pair + 1] - off;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->last_total > 0 && !ctx->last_written) {     // the match list may not be compacted yet
+    CK(ctx->out.ensure(sizeof(sfm_match_t) * ctx->last_total));
+    CK(launch_filter_write(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), ctx->last_n_pairs,
+                           ctx->last_ratio, ctx->last_floor, ctx->last_mult,
+                           ctx->min_dist.as<float>(), ctx->offsets.as<int64_t>(),
+                           ctx->out.as<sfm_match_t>(), ctx->last_total, ctx->stream));
+    ctx->launches += 1;
+    ctx->last_written = true;
+  }
+  int64_t n = n_all;
+  const int32_t* dsel = nullptr;
+  if (mask) {                                          // maskout_points(:943): keep mask[i] > 0
+    std::vector<int32_t> sel;
+    sel.reserve(static_cast<size_t>(n_all));
+    for (int64_t i = 0; i < n_all; ++i)
+      if (mask[i] > 0) sel.push_back(static_cast<int32_t>(i));
+    n = static_cast<int64_t>(sel.size());
+    CK(ctx->gsel.ensure(4 * static_cast<size_t>(n) + 4));
+    if (n) CK(cudaMemcpyAsync(ctx->gsel.p, sel.data(), 4 * static_cast<size_t>(n), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));            // sel is a local
+    dsel = ctx->gsel.as<int32_t>();
+  }
+  *n_out = n;
+  if (n == 0) return SFM_OK;
+  CK(ctx->gxy.ensure(sizeof(float) * 4 * static_cast<size_t>(n)));
+  CK(launch_gather_matched_points(ctx->out.as<sfm_match_t>() + off, dsel, n,
+                                  ctx->kp.as<float>() + 2 * ctx->kp_off[q],
+                                  ctx->kp.as<float>() + 2 * ctx->kp_off[t], ctx->gxy.as<float>(),
+                                  ctx->stream));
+  ctx->launches += 1;
+  return SFM_OK;
+}
+
+int sfm_get_matched_points(sfm_ctx* ctx, int pair, const uint8_t* mask, float* out_p1, float* out_p2,
+                           int64_t cap, int64_t* n_points) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!n_points) return fail(ctx, SFM_E_INVALID, "n_points must not be null");
+  int64_t n = 0;
+  int rc = gather_pair(ctx, pair, mask, &n);
+  if (rc) return rc;
+  *n_points = n;
+  if (n > cap || (n > 0 && (!out_p1 || !out_p2)))
+    return fail(ctx, SFM_E_CAPACITY, "point buffers too small; n_points holds the need");
+  if (n) {
+    CK(cudaMemcpyAsync(out_p1, ctx->gxy.p, 8 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_p2, ctx->gxy.as<float>() + 2 * n, 8 * static_cast<size_t>(n), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SFM_OK;
+}
+
+int sfm_reconstruct_pair(sfm_ctx* ctx, int pair, const double K[9], const double R1[9],
+                         const double T1[3], const double R2[9], const double T2[3],
+                         const uint8_t* mask, double* structure, int64_t cap, int64_t* n_points) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!K || !R1 || !T1 || !R2 || !T2 || !n_points) return fail(ctx, SFM_E_INVALID, "null camera argument");
+  int64_t n = 0;
+  int rc = gather_pair(ctx, pair, mask, &n);
+  if (rc) return rc;
+  *n_points = n;
+  if (n == 0) return fail(ctx, SFM_E_INVALID, "[Err]: empty 2d points.");     // :1122-1126
+  if (n > cap || !structure) return fail(ctx, SFM_E_CAPACITY, "structure buffer too small; n_points holds the need");
+  float P[24];
+  build_projection(K, R1, T1, P);
+  build_projection(K, R2, T2, P + 12);
+  CK(ctx->gP.ensure(sizeof P));
+  CK(ctx->gxyz.ensure(sizeof(double) * 3 * static_cast<size_t>(n)));
+  CK(cudaMemcpyAsync(ctx->gP.p, P, sizeof P, cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), 2, n, nullptr, ctx->gxyz.as<double>(),
+                        ctx->n_sms, ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(structure, ctx->gxyz.p, sizeof(double) * 3 * static_cast<size_t>(n), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
 }
 
 // ----------------------------------------------------------------------------- residuals

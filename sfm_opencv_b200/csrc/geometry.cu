@@ -8,6 +8,8 @@
 // Both are HBM-streaming kernels: one thread per point / observation, coalesced vector loads,
 // all state in registers, camera tables in shared memory.
 #include <cuda_runtime.h>
+
+#include "../../include/sfm_b200.h"
 #include <float.h>
 #include <stdint.h>
 
@@ -274,6 +276,31 @@ int geometry_grid(int64_t n, int n_sms) {
   const int64_t blocks = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(n_sms) * 8;   // 8 resident 256-thread CTAs per SM
   return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// get_matched_points (NViewReconstuct.cpp:989-1003) on the device: match m of a pair picks
+// kp_q[queryIdx].pt and kp_t[trainIdx].pt; sel (nullable) lists the matches that survive
+// maskout_points (:943).  Output is view-major [2][n][2], the triangulation kernel's layout.
+__global__ void gather_matched_points_kernel(const sfm_match_t* __restrict__ matches,
+                                             const int32_t* __restrict__ sel, int64_t n,
+                                             const float2* __restrict__ kp_q,
+                                             const float2* __restrict__ kp_t,
+                                             float2* __restrict__ xy) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 m = *reinterpret_cast<const int4*>(&matches[sel ? sel[i] : i]);
+  xy[i] = kp_q[m.x];
+  xy[n + i] = kp_t[m.y];
+}
+
+cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32_t* sel, int64_t n,
+                                         const float* kp_q, const float* kp_t, float* xy,
+                                         cudaStream_t s) {
+  if (n > 0)
+    gather_matched_points_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        matches, sel, n, reinterpret_cast<const float2*>(kp_q),
+        reinterpret_cast<const float2*>(kp_t), reinterpret_cast<float2*>(xy));
+  return cudaGetLastError();
 }
 
 cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,

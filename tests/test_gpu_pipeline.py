@@ -1,0 +1,96 @@
+"""GPU: matches -> points -> structure without a host round trip (sfm_upload_keypoints,
+sfm_get_matched_points, sfm_reconstruct_pair), on the bundled desktop dataset: the first-pair
+flow of the reference -- match_features, get_matched_points (NViewReconstuct.cpp:989-1003),
+findEssentialMat / recoverPose mask (:1022-1060, run by cv2 on the host as in the reference),
+maskout_points (:943), reconstruct (:1117-1159) -- and the all-matches flow of the later pairs."""
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+from oracle import matching as M
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def desktop(ctx, golden):
+    g = golden("desktop")
+    n = int(g["n_img"])
+    bank = [g[f"desc_{i}"] for i in range(n)]
+    kps = [g[f"kp_{i}"] for i in range(n)]
+    ctx.upload_descriptors(bank)
+    ctx.upload_keypoints(kps)
+    m, _, _ = ctx.match_pairs(M.consecutive_pairs(n))
+    return g, kps, m
+
+
+def test_gather_equals_host_gather(ctx, desktop):
+    g, kps, m = desktop
+    for p in range(len(m)):
+        p1, p2 = ctx.get_matched_points(p, len(m[p]))
+        assert np.array_equal(p1, kps[p][m[p]["queryIdx"]])
+        assert np.array_equal(p2, kps[p + 1][m[p]["trainIdx"]])
+    rng = np.random.default_rng(0)
+    mask = rng.integers(0, 3, len(m[1])).astype(np.uint8)       # values > 0 are kept
+    p1, p2 = ctx.get_matched_points(1, len(m[1]), mask)
+    assert np.array_equal(p1, kps[1][m[1]["queryIdx"]][mask > 0])
+    assert np.array_equal(p2, kps[2][m[1]["trainIdx"]][mask > 0])
+
+
+def test_first_pair_pose_mask_reconstruct(ctx, desktop):
+    import cv2
+    g, kps, m = desktop
+    K = G.K_REFERENCE
+    assert len(m[0]) == 871
+    p1, p2 = ctx.get_matched_points(0, len(m[0]))
+    focal, pp = 0.5 * (K[0, 0] + K[1, 1]), (K[0, 2], K[1, 2])
+    cv2.setRNGSeed(0)
+    E, mask = cv2.findEssentialMat(p1, p2, focal, pp, cv2.RANSAC, 0.999, 1.0)
+    _, R, T, mask = cv2.recoverPose(E, p1, p2, focal=focal, pp=pp, mask=mask)
+    mask = mask.reshape(-1)
+    assert mask.sum() > 500
+    xyz = ctx.reconstruct_pair(0, len(m[0]), K, np.eye(3), np.zeros(3), R, T, mask)
+    ref, _ = G.reconstruct(K, np.eye(3), np.zeros(3), R, T, p1[mask > 0], p2[mask > 0])
+    assert xyz.shape == ref.shape == (int((mask > 0).sum()), 3)
+    assert G.point_rel_err(xyz, ref).max() < REL_TOL
+    # the same through the host-array entry point
+    import sfm_opencv_b200 as sfm
+    host = sfm.reconstruct(ctx, K, np.eye(3), np.zeros(3), R, T, p1[mask > 0], p2[mask > 0])
+    assert G.point_rel_err(xyz, host).max() < 1e-6
+
+
+def test_later_pairs_use_all_matches(ctx, desktop):
+    """Later frames triangulate ALL matches of the pair (NViewReconstuct.cpp:1441), outliers
+    included; parity is asserted on the geometrically consistent ones (the outliers' rays do
+    not meet: their DLT systems are ill-conditioned and cv2's own float32 output is noise)."""
+    import cv2
+    g, kps, m = desktop
+    K = G.K_REFERENCE
+    focal, pp = 0.5 * (K[0, 0] + K[1, 1]), (K[0, 2], K[1, 2])
+    for p in (1, 2, 3):
+        p1, p2 = kps[p][m[p]["queryIdx"]], kps[p + 1][m[p]["trainIdx"]]
+        cv2.setRNGSeed(p)
+        E, mask = cv2.findEssentialMat(p1, p2, focal, pp, cv2.RANSAC, 0.999, 1.0)
+        _, R, T, mask = cv2.recoverPose(E, p1, p2, focal=focal, pp=pp, mask=mask)
+        inl = mask.reshape(-1) > 0
+        xyz = ctx.reconstruct_pair(p, len(m[p]), K, np.eye(3), np.zeros(3), R, T)
+        ref, _ = G.reconstruct(K, np.eye(3), np.zeros(3), R, T, p1, p2)
+        assert xyz.shape == ref.shape == (len(m[p]), 3) and inl.sum() > 50
+        assert G.point_rel_err(xyz[inl], ref[inl]).max() < REL_TOL
+
+
+def test_errors(ctx, desktop):
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    g, kps, m = desktop
+    K = G.K_REFERENCE
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.reconstruct_pair(0, len(m[0]), K, np.eye(3), np.zeros(3), np.eye(3), np.ones(3),
+                             np.zeros(len(m[0]), np.uint8))
+    assert e.value.code == _capi.SFM_E_INVALID                    # "[Err]: empty 2d points."
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.get_matched_points(0, 3)
+    assert e.value.code == _capi.SFM_E_CAPACITY
+    with pytest.raises(sfm.SfmError):
+        ctx.get_matched_points(99, 10)

@@ -54,3 +54,15 @@ def test_observation_order_is_camera_major():
     cam, pt, obs = G.enumerate_observations(ids, kps)
     assert list(cam) == [0, 0, 1, 1] and list(pt) == [0, 2, 1, 0]
     assert obs.tolist() == [[0, 1], [4, 5], [12, 13], [14, 15]]
+
+
+def test_projection_build_is_bitwise_cv_gemm():
+    """proj = fK * proj (NViewReconstuct.cpp:1141-1143) is a cv::gemm on CV_32F operands."""
+    import cv2
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        R, _ = cv2.Rodrigues(rng.normal(0, 0.5, 3))
+        T = rng.normal(0, 3, 3)
+        RT = np.concatenate([R.astype(np.float32), T.astype(np.float32).reshape(3, 1)], 1)
+        want = cv2.gemm(G.K_REFERENCE.astype(np.float32), RT, 1.0, None, 0.0)
+        assert np.array_equal(G.build_projection(G.K_REFERENCE, R, T), want)
