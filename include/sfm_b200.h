@@ -204,6 +204,17 @@ SFM_API int sfm_reproject_residuals(sfm_ctx* ctx, const double intr[4], const do
                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
                             double huber_delta, double* resid, double* huber_cost);
 
+/* Jacobians of the same residual blocks with respect to the three parameter blocks Ceres is
+ * given at NViewReconstuct.cpp:1202-1209 -- what AutoDiffCostFunction<ReprojectCost, 2, 4, 6, 3>
+ * computes with Jets.  jac is [n_obs][2][13] doubles, row-major: for each of the two residual
+ * rows the derivatives with respect to (fx, fy, cx, cy | angle-axis(3), t(3) | X, Y, Z).
+ * resid is nullable.  iters > 0 keeps the inputs on the device, launches the kernel `iters`
+ * times and reports the mean CUDA-event time per launch in ms_per_launch (nullable). */
+SFM_API int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
+                            const double* pts, int64_t n_pts, const int32_t* cam_idx,
+                            const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                            double* resid, double* jac, int iters, float* ms_per_launch);
+
 /* ---- output files: save_structure() / write_ply_binary() ---------------------------- */
 
 /* Writes the file save_structure() writes (NViewReconstuct.cpp:186-227) byte for byte as

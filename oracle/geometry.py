@@ -143,6 +143,54 @@ def reproject_residuals(intr, ext, pts, cam_idx, pt_idx, obs_xy) -> np.ndarray:
     return np.stack([u - obs[:, 0], v - obs[:, 1]], 1)
 
 
+def reproject_jacobians(intr, ext, pts, cam_idx, pt_idx) -> np.ndarray:
+    """d(residual)/d(intrinsic | extrinsic | point) of ReprojectCost (NViewReconstuct.cpp:151-183)
+    in the parameter-block order of :1202-1209 -- what ceres::AutoDiffCostFunction<ReprojectCost,
+    2, 4, 6, 3> evaluates.  Closed form of the same function (both AngleAxisRotatePoint
+    branches); pinned in tests/test_oracle_geometry.py against cv2.projectPoints' Jacobian and
+    against central differences of :func:`reproject_residuals`.  Returns [n_obs, 2, 13] float64."""
+    intr = np.asarray(intr, np.float64)
+    ext = np.asarray(ext, np.float64).reshape(-1, 6)
+    pts = np.asarray(pts, np.float64).reshape(-1, 3)
+    e = ext[np.asarray(cam_idx)]
+    X = pts[np.asarray(pt_idx)]
+    w, t = e[:, :3], e[:, 3:]
+    n = X.shape[0]
+    theta2 = (w * w).sum(-1)
+    big = theta2 > np.finfo(np.float64).eps
+    theta = np.sqrt(np.where(big, theta2, 1.0))
+    wh = w / theta[:, None]
+    s, c = np.sin(theta), np.cos(theta)
+    p = angle_axis_rotate(w, X) + t
+    x, y, iz = p[:, 0] / p[:, 2], p[:, 1] / p[:, 2], 1.0 / p[:, 2]
+    fx, fy = intr[0], intr[1]
+    A = np.zeros((n, 2, 3))
+    A[:, 0, 0] = fx * iz; A[:, 0, 2] = -fx * x * iz
+    A[:, 1, 1] = fy * iz; A[:, 1, 2] = -fy * y * iz
+    # rotation matrix (dp/dX) and dp/dw, column by column
+    I = np.eye(3)
+    wxX = np.cross(wh, X)
+    d = (wh * X).sum(-1)
+    dpdw = np.zeros((n, 3, 3))
+    R = np.zeros((n, 3, 3))
+    for q in range(3):
+        eq = np.broadcast_to(I[q], (n, 3))
+        g = (eq - wh * wh[:, q:q + 1]) / theta[:, None]
+        far = (-s * wh[:, q])[:, None] * X + s[:, None] * np.cross(g, X) + (c * wh[:, q])[:, None] * wxX \
+            + (1.0 - c)[:, None] * (g * d[:, None] + wh * (g * X).sum(-1, keepdims=True)) \
+            + (s * wh[:, q] * d)[:, None] * wh
+        near = np.cross(eq, X)
+        dpdw[:, :, q] = np.where(big[:, None], far, near)
+        R[:, :, q] = angle_axis_rotate(w, eq)                 # R e_q = column q
+    J = np.zeros((n, 2, 13))
+    J[:, 0, 0] = x; J[:, 0, 2] = 1.0
+    J[:, 1, 1] = y; J[:, 1, 3] = 1.0
+    J[:, :, 4:7] = A @ dpdw
+    J[:, :, 7:10] = A
+    J[:, :, 10:13] = A @ R
+    return J
+
+
 def huber_cost(resid: np.ndarray, delta: float = 4.0) -> float:
     """0.5 * sum rho(s), s = |r|^2, ceres::HuberLoss(delta): rho = s (s <= delta^2),
     2*delta*sqrt(s) - delta^2 otherwise (NViewReconstuct.cpp:1184)."""

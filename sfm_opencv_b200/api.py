@@ -266,6 +266,29 @@ class Context:
         self._check(self._lib.sfm_reproject_residuals(*args))
         return resid, (cost.value if want_cost else None)
 
+    def reproject_jacobians(self, intr, ext, pts, cam_idx, pt_idx, obs_xy, want_resid=True,
+                            iters=0):
+        """Residuals and their Jacobians (what Ceres' autodiff derives from ReprojectCost,
+        NViewReconstuct.cpp:1202): returns (resid [n,2] or None, J [n,2,13]) with the columns
+        ordered (fx, fy, cx, cy | angle-axis(3), t(3) | X, Y, Z); with iters > 0 also the mean
+        kernel time in ms."""
+        intr = np.ascontiguousarray(intr, np.float64).reshape(4)
+        ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 6)
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        cam_idx = np.ascontiguousarray(cam_idx, np.int32)
+        pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2)
+        n_obs = cam_idx.shape[0]
+        resid = np.empty((n_obs, 2), np.float64) if want_resid else None
+        jac = np.empty((n_obs, 2, 13), np.float64)
+        ms = C.c_float(0)
+        self._check(self._lib.sfm_reproject_jacobians(
+            self._h, _ptr(intr, C.c_double), _ptr(ext, C.c_double), ext.shape[0],
+            _ptr(pts, C.c_double), pts.shape[0], _ptr(cam_idx, C.c_int32), _ptr(pt_idx, C.c_int32),
+            _ptr(obs_xy, C.c_float), n_obs, _ptr(resid, C.c_double) if want_resid and n_obs else None,
+            _ptr(jac, C.c_double) if n_obs else None, iters, C.byref(ms)))
+        return (resid, jac, ms.value) if iters > 0 else (resid, jac)
+
     # ------------------------------------------------------------------ timing hooks
     def timer_start(self):
         self._check(self._lib.sfm_timer_start(self._h))

@@ -46,6 +46,10 @@ cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32
                                          const float* kp_q, const float* kp_t, float* xy,
                                          cudaStream_t s);
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
+cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam, double* cam,
+                             double* jtab, const double* pts, const int32_t* cam_idx,
+                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                             double* resid, double* jac, int n_sms, bool tables, cudaStream_t s);
 cudaError_t launch_residuals(const double intr[4], const double* cam, const double* pts,
                              const int32_t* cam_idx, const int32_t* pt_idx, const float* obs_xy,
                              int64_t n_obs, double huber_delta, double* resid, double* block_cost,
@@ -123,6 +127,7 @@ struct sfm_ctx {
   std::vector<int64_t> kp_off;
   bool kp_ready = false;
   // geometry scratch
+  DevBuf gjtab, gjac;
   DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
 };
 
@@ -213,7 +218,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
-                    &ctx->partial, &ctx->kp, &ctx->gsel, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -630,6 +635,66 @@ int sfm_triangulate_batch_timed(sfm_ctx* ctx, const float* P, const float* xy, i
                                 float* ms_per_launch) {
   if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
   return triangulate_common(ctx, P, xy, n_views, n_pts, X4, xyz, iters, ms_per_launch);
+}
+
+// ----------------------------------------------------------------------------- Jacobians
+int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
+                            const double* pts, int64_t n_pts, const int32_t* cam_idx,
+                            const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                            double* resid, double* jac, int iters, float* ms_per_launch) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!intr || !ext || !pts || n_cam <= 0 || n_pts <= 0)
+    return fail(ctx, SFM_E_INVALID, "null camera / point tables");
+  if (n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)))
+    return fail(ctx, SFM_E_INVALID, "null observation arrays");
+  for (int64_t k = 0; k < n_obs; ++k)
+    if (cam_idx[k] < 0 || cam_idx[k] >= n_cam || pt_idx[k] < 0 || pt_idx[k] >= n_pts)
+      return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
+  if (n_obs == 0) return SFM_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->gext.ensure(sizeof(double) * 6 * n_cam));
+  CK(ctx->gcam.ensure(sizeof(double) * 12 * n_cam));
+  CK(ctx->gjtab.ensure(sizeof(double) * 8 * n_cam));
+  CK(ctx->gpts.ensure(sizeof(double) * 3 * n_pts));
+  CK(ctx->gci.ensure(4 * n_obs));
+  CK(ctx->gpi.ensure(4 * n_obs));
+  CK(ctx->gobs.ensure(8 * n_obs));
+  CK(ctx->gres.ensure(16 * n_obs));
+  CK(ctx->gjac.ensure(sizeof(double) * 26 * static_cast<size_t>(n_obs)));
+  CK(cudaMemcpyAsync(ctx->gext.p, ext, sizeof(double) * 6 * n_cam, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gpts.p, pts, sizeof(double) * 3 * n_pts, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gci.p, cam_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gpi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->gobs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  double* dres = (resid || iters > 0) ? ctx->gres.as<double>() : nullptr;
+  const int reps = iters > 0 ? iters : 1;
+  auto launch = [&](bool tables) {
+    return launch_jacobians(intr, ctx->gext.as<double>(), n_cam, ctx->gcam.as<double>(),
+                            ctx->gjtab.as<double>(), ctx->gpts.as<double>(), ctx->gci.as<int32_t>(),
+                            ctx->gpi.as<int32_t>(), ctx->gobs.as<float>(), n_obs, dres,
+                            ctx->gjac.as<double>(), ctx->n_sms, tables, ctx->stream);
+  };
+  if (iters > 0) {          // tables + one untimed warm-up launch
+    CK(launch(true));
+    ctx->launches += 3;
+  }
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  for (int r = 0; r < reps; ++r) {
+    CK(launch(iters <= 0));
+    ctx->launches += iters <= 0 ? 3 : 1;
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (resid) CK(cudaMemcpyAsync(resid, ctx->gres.p, 16 * n_obs, cudaMemcpyDeviceToHost, ctx->stream));
+  if (jac)
+    CK(cudaMemcpyAsync(jac, ctx->gjac.p, sizeof(double) * 26 * static_cast<size_t>(n_obs),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ms_per_launch) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    *ms_per_launch = ms / reps;
+  }
+  return SFM_OK;
 }
 
 // ------------------------------------------------------------- match list -> 3-D structure

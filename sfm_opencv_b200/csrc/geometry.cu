@@ -256,6 +256,125 @@ residual_kernel(double fx, double fy, double cx, double cy, const double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Jacobians of ReprojectCost (NViewReconstuct.cpp:151-183) with respect to its three
+// parameter blocks, in the order Ceres sees them (:1202-1209): intrinsic (fx, fy, cx, cy),
+// extrinsic (angle-axis, translation), point.  This is what AutoDiffCostFunction<ReprojectCost,
+// 2, 4, 6, 3> derives with Jets; here it is the closed form of the same function, including
+// the small-angle branch of ceres::AngleAxisRotatePoint (p = X + w x X).
+//
+// Second camera table: 8 doubles per camera {w_hat(3), theta, sin, cos, big-angle flag, 0}.
+__global__ void camera_jac_table_kernel(const double* __restrict__ ext, int n_cam,
+                                        double* __restrict__ tab) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cam) return;
+  const double w0 = ext[6 * c + 0], w1 = ext[6 * c + 1], w2 = ext[6 * c + 2];
+  const double theta2 = w0 * w0 + w1 * w1 + w2 * w2;
+  double* o = tab + 8 * c;
+  if (theta2 > DBL_EPSILON) {
+    const double theta = sqrt(theta2), ti = 1.0 / theta;
+    o[0] = w0 * ti; o[1] = w1 * ti; o[2] = w2 * ti;
+    o[3] = theta; o[4] = sin(theta); o[5] = cos(theta); o[6] = 1.0;
+  } else {
+    o[0] = w0; o[1] = w1; o[2] = w2;
+    o[3] = 0.0; o[4] = 0.0; o[5] = 1.0; o[6] = 0.0;
+  }
+  o[7] = 0.0;
+}
+
+constexpr int kJacThreads = 128;
+constexpr int kJacCols = 13;                       // 4 + 6 + 3 parameters
+constexpr int kJacRow = 2 * kJacCols;              // doubles per observation
+constexpr int kJacPad = kJacRow + 1;               // shared-memory row stride (bank spread)
+
+// One observation per thread; the 26 doubles of every observation are staged in shared
+// memory so that the block writes its contiguous 128 x 208-byte output range coalesced.
+__global__ void __launch_bounds__(kJacThreads)
+jacobian_kernel(double fx, double fy, double cx, double cy, const double* __restrict__ cam,
+                const double* __restrict__ jtab, const double* __restrict__ pts,
+                const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pt_idx,
+                const float* __restrict__ obs_xy, int64_t n_obs, double* __restrict__ resid,
+                double* __restrict__ jac) {
+  __shared__ double s_j[kJacThreads * kJacPad];
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kJacThreads; base < n_obs;
+       base += static_cast<int64_t>(gridDim.x) * kJacThreads) {
+    const int64_t k = base + threadIdx.x;
+    if (k < n_obs) {
+      const int c = cam_idx[k], j = pt_idx[k];
+      const double* R = cam + 12 * static_cast<int64_t>(c);
+      const double* W = jtab + 8 * static_cast<int64_t>(c);
+      const double* Xp = pts + 3 * static_cast<int64_t>(j);
+      const double X[3] = {__ldg(Xp), __ldg(Xp + 1), __ldg(Xp + 2)};
+      double Rm[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rm[i] = __ldg(R + i);
+      const double p0 = Rm[0] * X[0] + Rm[1] * X[1] + Rm[2] * X[2] + __ldg(R + 9);
+      const double p1 = Rm[3] * X[0] + Rm[4] * X[1] + Rm[5] * X[2] + __ldg(R + 10);
+      const double p2 = Rm[6] * X[0] + Rm[7] * X[1] + Rm[8] * X[2] + __ldg(R + 11);
+      const double x = p0 / p2, y = p1 / p2, iz = 1.0 / p2;
+      if (resid != nullptr) {
+        const float2 o = reinterpret_cast<const float2*>(obs_xy)[k];
+        reinterpret_cast<double2*>(resid)[k] = make_double2(fx * x + cx - static_cast<double>(o.x),
+                                                            fy * y + cy - static_cast<double>(o.y));
+      }
+      // d(residual)/d(p): rows (fx/z, 0, -fx x/z), (0, fy/z, -fy y/z)
+      const double a00 = fx * iz, a02 = -fx * x * iz, a11 = fy * iz, a12 = -fy * y * iz;
+      double* o = s_j + threadIdx.x * kJacPad;
+      // intrinsic block
+      o[0] = x;   o[1] = 0.0; o[2] = 1.0; o[3] = 0.0;
+      o[kJacCols + 0] = 0.0; o[kJacCols + 1] = y; o[kJacCols + 2] = 0.0; o[kJacCols + 3] = 1.0;
+      // extrinsic block: angle-axis
+      const double wh[3] = {__ldg(W), __ldg(W + 1), __ldg(W + 2)};
+      const double theta = __ldg(W + 3), st = __ldg(W + 4), ct = __ldg(W + 5);
+      const bool big = __ldg(W + 6) != 0.0;
+      const double wxX[3] = {wh[1] * X[2] - wh[2] * X[1], wh[2] * X[0] - wh[0] * X[2],
+                             wh[0] * X[1] - wh[1] * X[0]};
+      const double d = wh[0] * X[0] + wh[1] * X[1] + wh[2] * X[2];
+      const double ti = big ? 1.0 / theta : 0.0, oc = 1.0 - ct;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        // e_q x X
+        const double exX[3] = {q == 1 ? X[2] : (q == 2 ? -X[1] : 0.0),
+                               q == 2 ? X[0] : (q == 0 ? -X[2] : 0.0),
+                               q == 0 ? X[1] : (q == 1 ? -X[0] : 0.0)};
+        double dp[3];
+        if (big) {
+          // g = (e_q - w_hat w_hat_q) / theta;  dp = -s w_q X + s (g x X) + c w_q (w_hat x X)
+          //      + (1 - c) (g d + w_hat (g . X)) + s w_q d w_hat
+          const double wq = wh[q];
+          const double gX = (X[q] - d * wq) * ti;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const double g_i = ((i == q ? 1.0 : 0.0) - wh[i] * wq) * ti;
+            const double gxX_i = (exX[i] - wq * wxX[i]) * ti;
+            dp[i] = -st * wq * X[i] + st * gxX_i + ct * wq * wxX[i] + oc * (g_i * d + wh[i] * gX) +
+                    st * wq * d * wh[i];
+          }
+        } else {
+          dp[0] = exX[0]; dp[1] = exX[1]; dp[2] = exX[2];
+        }
+        o[4 + q] = a00 * dp[0] + a02 * dp[2];
+        o[kJacCols + 4 + q] = a11 * dp[1] + a12 * dp[2];
+      }
+      // extrinsic block: translation (dp/dt = I)
+      o[7] = a00; o[8] = 0.0; o[9] = a02;
+      o[kJacCols + 7] = 0.0; o[kJacCols + 8] = a11; o[kJacCols + 9] = a12;
+      // point block (dp/dX = R)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        o[10 + q] = a00 * Rm[q] + a02 * Rm[6 + q];
+        o[kJacCols + 10 + q] = a11 * Rm[3 + q] + a12 * Rm[6 + q];
+      }
+    }
+    __syncthreads();
+    const int64_t rows = min(static_cast<int64_t>(kJacThreads), n_obs - base);
+    double* dst = jac + base * kJacRow;
+    for (int64_t e = threadIdx.x; e < rows * kJacRow; e += kJacThreads)
+      __stcs(dst + e, s_j[(e / kJacRow) * kJacPad + (e % kJacRow)]);
+    __syncthreads();
+  }
+}
+
 // fixed-order sum of the per-block partial costs (deterministic), result = 0.5 * sum
 __global__ void __launch_bounds__(256)
 cost_sum_kernel(const double* __restrict__ block_cost, int n, double* __restrict__ out) {
@@ -311,6 +430,21 @@ cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int
 
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s) {
   camera_table_kernel<<<(n_cam + 127) / 128, 128, 0, s>>>(ext, n_cam, cam);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam, double* cam,
+                             double* jtab, const double* pts, const int32_t* cam_idx,
+                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                             double* resid, double* jac, int n_sms, bool tables, cudaStream_t s) {
+  if (tables) {
+    camera_table_kernel<<<(n_cam + 127) / 128, 128, 0, s>>>(ext, n_cam, cam);
+    camera_jac_table_kernel<<<(n_cam + 127) / 128, 128, 0, s>>>(ext, n_cam, jtab);
+  }
+  const int64_t blocks = (n_obs + kJacThreads - 1) / kJacThreads;
+  const int grid = static_cast<int>(blocks < 16ll * n_sms ? (blocks > 0 ? blocks : 1) : 16ll * n_sms);
+  jacobian_kernel<<<grid, kJacThreads, 0, s>>>(intr[0], intr[1], intr[2], intr[3], cam, jtab, pts,
+                                               cam_idx, pt_idx, obs_xy, n_obs, resid, jac);
   return cudaGetLastError();
 }
 

@@ -167,3 +167,36 @@ def test_bundle_adjustment_residuals_api(ctx):
     assert r.shape == rr.shape and np.abs(r - rr).max() <= REL_TOL * max(1.0, np.abs(rr).max())
     c = G.huber_cost(rr, 4.0)
     assert abs(cost - c) <= 1e-9 * c and abs(rmse - np.sqrt(c / len(cam))) <= 1e-9
+
+
+def test_jacobians_vs_oracle(ctx):
+    """sfm_reproject_jacobians: what Ceres' autodiff derives from ReprojectCost (:1202)."""
+    sc = synth.scene(3000, 4, seed=21)
+    ext = sc["ext"].copy()
+    ext[0, :3] = [1e-10, -2e-10, 3e-11]                       # small-angle branch camera
+    cam = np.repeat(np.arange(4), 3000).astype(np.int32)
+    pt = np.tile(np.arange(3000), 4).astype(np.int32)
+    perm = np.random.default_rng(0).permutation(cam.size)[:11111]     # ragged count, mixed order
+    cam, pt = cam[perm], pt[perm]
+    obs = sc["xy"].reshape(-1, 2)[perm]
+    r, J = ctx.reproject_jacobians(sc["intr"], ext, sc["X"], cam, pt, obs)
+    ref_r = G.reproject_residuals(sc["intr"], ext, sc["X"], cam, pt, obs)
+    ref_J = G.reproject_jacobians(sc["intr"], ext, sc["X"], cam, pt)
+    assert J.shape == (11111, 2, 13)
+    assert np.abs(r - ref_r).max() < REL_TOL * 1000.0
+    # Jacobian entries span 1e-3 .. 1e4: relative to the row's largest entry
+    scale = np.abs(ref_J).max(axis=2, keepdims=True)
+    assert (np.abs(J - ref_J) / scale).max() < 1e-9
+    # structural zeros and ones are exact
+    assert np.array_equal(J[:, 0, [1, 3, 8]], np.zeros((11111, 3))) and np.array_equal(J[:, 0, 2], np.ones(11111))
+
+
+def test_jacobians_single_observation_and_timed(ctx):
+    sc = synth.scene(10, 2, seed=4)
+    cam = np.array([1], np.int32); pt = np.array([7], np.int32)
+    r, J = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt, sc["xy"][1, 7:8])
+    ref = G.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt)
+    assert np.allclose(J, ref, rtol=1e-10, atol=1e-12)
+    cam = np.repeat(np.arange(2), 10).astype(np.int32); pt = np.tile(np.arange(10), 2).astype(np.int32)
+    r2, J2, ms = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt, sc["xy"].reshape(-1, 2), iters=3)
+    assert ms > 0 and np.allclose(J2, G.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt), rtol=1e-10, atol=1e-12)

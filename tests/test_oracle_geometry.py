@@ -66,3 +66,61 @@ def test_projection_build_is_bitwise_cv_gemm():
         RT = np.concatenate([R.astype(np.float32), T.astype(np.float32).reshape(3, 1)], 1)
         want = cv2.gemm(G.K_REFERENCE.astype(np.float32), RT, 1.0, None, 0.0)
         assert np.array_equal(G.build_projection(G.K_REFERENCE, R, T), want)
+
+
+def _jac_scene():
+    sc = synth.scene(150, 3, seed=1)
+    ext = sc["ext"].copy()
+    ext[0, :3] = [1e-10, -2e-10, 3e-11]              # camera 0: small-angle branch
+    cam = np.repeat(np.arange(3), 150).astype(np.int32)
+    pt = np.tile(np.arange(150), 3).astype(np.int32)
+    return sc, ext, cam, pt
+
+
+def test_jacobian_oracle_vs_cv2_projectpoints():
+    """cv2.projectPoints differentiates the same projection analytically (OpenCV's own
+    Rodrigues derivative): an independent pin for d/d(angle-axis), d/dt, d/df, d/dc."""
+    import cv2
+    sc, ext, cam, pt = _jac_scene()
+    intr = sc["intr"]
+    J = G.reproject_jacobians(intr, ext, sc["X"], cam, pt)
+    K = np.array([[intr[0], 0, intr[2]], [0, intr[1], intr[3]], [0, 0, 1.0]])
+    for c in (1, 2):
+        _, jac = cv2.projectPoints(sc["X"], ext[c, :3], ext[c, 3:], K, None)
+        Jcv = jac.reshape(-1, 2, jac.shape[1])
+        Jc = J[cam == c]
+        scale = 1.0 + np.abs(Jcv[:, :, :10]).max()
+        assert np.abs(Jc[:, :, 4:7] - Jcv[:, :, 0:3]).max() < 1e-12 * scale
+        assert np.abs(Jc[:, :, 7:10] - Jcv[:, :, 3:6]).max() < 1e-12 * scale
+        assert np.abs(Jc[:, 0, 0] - Jcv[:, 0, 6]).max() < 1e-12 and np.abs(Jc[:, 1, 1] - Jcv[:, 1, 7]).max() < 1e-12
+        assert np.array_equal(Jc[:, :, 2:4], Jcv[:, :, 8:10])
+
+
+def test_jacobian_oracle_vs_central_differences():
+    sc, ext, cam, pt = _jac_scene()
+    intr, X, obs = sc["intr"], sc["X"], sc["xy"].reshape(-1, 2)
+    J = G.reproject_jacobians(intr, ext, X, cam, pt)
+    h = 1e-6
+
+    def res(i, e, x):
+        return G.reproject_residuals(i, e, x, cam, pt, obs)
+    num = np.zeros_like(J)
+    for k in range(4):
+        d = np.zeros(4); d[k] = h
+        num[:, :, k] = (res(intr + d, ext, X) - res(intr - d, ext, X)) / (2 * h)
+    for k in range(6):
+        d = np.zeros((1, 6)); d[0, k] = h
+        num[:, :, 4 + k] = (res(intr, ext + d, X) - res(intr, ext - d, X)) / (2 * h)
+    for k in range(3):
+        d = np.zeros((1, 3)); d[0, k] = h
+        num[:, :, 10 + k] = (res(intr, ext, X + d) - res(intr, ext, X - d)) / (2 * h)
+    err = np.abs(J - num) / (1.0 + np.abs(num))
+    big = cam != 0                      # differencing across camera 0's branch switch is meaningless
+    assert err[big].max() < 1e-5
+    assert err[~big][:, :, [0, 1, 2, 3, 7, 8, 9, 10, 11, 12]].max() < 1e-5
+    # small-angle branch: d(X + w x X)/dw = -[X]x, times d(residual)/dp
+    Xs = X[pt[~big]]
+    A = J[~big][:, :, 7:10]
+    for q in range(3):
+        e = np.zeros(3); e[q] = 1.0
+        assert np.allclose(J[~big][:, :, 4 + q], np.einsum("nij,nj->ni", A, np.cross(e, Xs)), rtol=1e-12, atol=1e-12)
