@@ -188,6 +188,12 @@ def extras(ctx, hbm_gbs, peak_src):
     except Exception as e:                                   # pragma: no cover
         out["pair_65536"] = {"error": str(e)}
     try:
+        fp64_peak = ctx.probe_fp64_peak(4000)                # measured DFMA rate, TFLOP/s
+        out["fp64_probe_tflops"] = fp64_peak
+    except Exception as e:                                   # pragma: no cover
+        fp64_peak = None
+        out["fp64_probe"] = {"error": str(e)}
+    try:
         n = 4_000_000
         for V in (2, 8):
             sc = synth.scene(n, V)
@@ -199,6 +205,12 @@ def extras(ctx, hbm_gbs, peak_src):
                 "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
                              "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
                              "bytes_per_point": 8 * V + 16, "peak_source": peak_src}}
+            if fp64_peak:
+                # the kernel's real ceiling: ~(20 V + 170) fp64 FMA/MUL per point
+                fl = 2.0 * (20 * V + 170) * n / (ms * 1e-3) / 1e12
+                out[f"triangulate_4M_v{V}"]["fp64"] = {"achieved_tflops": fl, "peak_tflops": fp64_peak,
+                                                       "frac": fl / fp64_peak,
+                                                       "note": "fp64-pipe bound; peak = in-run DFMA probe"}
             cam, pt = synth.observations_camera_major(n, V)
             _, _, ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt,
                                                sc["xy"].reshape(-1, 2), want_cost=False,
@@ -210,9 +222,35 @@ def extras(ctx, hbm_gbs, peak_src):
                              "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
                              "bytes_per_obs": 32, "bytes_per_point": 24,
                              "peak_source": peak_src}}
+            if V == 2:
+                # Jacobians of the same residual blocks: 16 B in + 16 B residual + 208 B of
+                # derivatives per observation, 24 B per distinct point
+                _, _, ms = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt,
+                                                   sc["xy"].reshape(-1, 2), want_resid=False, iters=10)
+                b = (16 + 16 + 208) * n * V + 24 * n
+                out["jacobians_4M_v2"] = {
+                    "ms": ms, "obs_per_s": n * V / (ms * 1e-3),
+                    "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
+                                 "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
+                                 "bytes_per_obs": 240, "bytes_per_point": 24, "peak_source": peak_src}}
             del sc
     except Exception as e:                                   # pragma: no cover
         out["geometry"] = {"error": str(e)}
+    try:
+        # the live reference configuration: binary descriptors, NORM_HAMMING2 (AKAZE-sized: 61 B)
+        rng = np.random.default_rng(0)
+        nb, nd = 16, 8192
+        bank = [rng.integers(0, 256, (nd, 61), dtype=np.uint8) for _ in range(nb)]
+        ctx.upload_descriptors(bank, norm="hamming2")
+        pairs = all_pairs(nb)
+        ctx.match_pairs_resident(pairs)
+        best = min(ctx.match_pairs_resident(pairs)[1:] for _ in range(3))
+        out["hamming2_16x8192_allpairs"] = {
+            "knn_ms": best[0], "total_ms": best[1], "image_pairs_per_s": len(pairs) / (best[1] * 1e-3),
+            "descriptor_pairs_per_s": len(pairs) * nd * nd / (best[0] * 1e-3),
+            "note": "CUDA-core XOR/POPC kernel, 16 words per descriptor pair"}
+    except Exception as e:                                   # pragma: no cover
+        out["hamming2"] = {"error": str(e)}
     return out
 
 

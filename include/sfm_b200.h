@@ -254,6 +254,10 @@ SFM_API int sfm_reproject_residuals_timed(sfm_ctx* ctx, const double intr[4], co
  * measured int8 tensor peak the matching roofline is quoted against. */
 SFM_API int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops);
 
+/* Bare fp64 FMA issue-rate probe (registers only): achieved TFLOP/s, FMA counted as 2.  The
+ * measured ceiling of the triangulation kernel, which is fp64-pipe bound. */
+SFM_API int sfm_probe_fp64_peak(sfm_ctx* ctx, int iters, double* tflops);
+
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 SFM_API int64_t sfm_launch_count(const sfm_ctx* ctx);
 

@@ -302,6 +302,11 @@ class Context:
     def sync(self):
         self._check(self._lib.sfm_sync(self._h))
 
+    def probe_fp64_peak(self, iters: int = 4000) -> float:
+        t = C.c_double(0)
+        self._check(self._lib.sfm_probe_fp64_peak(self._h, iters, C.byref(t)))
+        return t.value
+
     def probe_i8_peak(self, iters: int = 2000) -> float:
         tops = C.c_double(0)
         self._check(self._lib.sfm_probe_i8_peak(self._h, iters, C.byref(tops)))

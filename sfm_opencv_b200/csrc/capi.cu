@@ -45,6 +45,7 @@ cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int
 cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32_t* sel, int64_t n,
                                          const float* kp_q, const float* kp_t, float* xy,
                                          cudaStream_t s);
+cudaError_t launch_fp64_peak(int iters, int n_sms, double* sink, cudaStream_t s);
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
 cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam, double* cam,
                              double* jtab, const double* pts, const int32_t* cam_idx,
@@ -933,6 +934,23 @@ int sfm_probe_i8_peak(sfm_ctx* ctx, int iters, double* tops) {
   CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   const double ops = 2.0 * 128.0 * 256.0 * 32.0 * 4.0 * (iters > 0 ? iters : (-iters) >> 4) * ctx->n_sms;   // probe tile 128x256
   *tops = ops / (ms * 1e-3) / 1e12;
+  return SFM_OK;
+}
+
+int sfm_probe_fp64_peak(sfm_ctx* ctx, int iters, double* tflops) {
+  if (!ctx) return SFM_E_INVALID;
+  if (iters <= 0 || !tflops) return fail(ctx, SFM_E_INVALID, "bad probe arguments");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->gcost.ensure(8));
+  CK(launch_fp64_peak(iters, ctx->n_sms, ctx->gcost.as<double>(), ctx->stream));   // warm-up
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CK(launch_fp64_peak(iters, ctx->n_sms, ctx->gcost.as<double>(), ctx->stream));
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 2;
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  *tflops = 2.0 * 8.0 * iters * 256.0 * 8.0 * ctx->n_sms / (ms * 1e-3) / 1e12;   // FMA = 2 flop
   return SFM_OK;
 }
 

@@ -390,6 +390,28 @@ cost_sum_kernel(const double* __restrict__ block_cost, int n, double* __restrict
   if (threadIdx.x == 0) *out = 0.5 * s[0];
 }
 
+// Bare fp64 issue-rate probe: 8 independent DFMA chains per thread, registers only.  The
+// triangulation kernel is bound by this pipe, not by HBM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = seed + k + threadIdx.x;
+  const double m = 1.0 + seed * 1e-9, c = seed * 1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += a[k];
+  if (t == 12345.678) sink[0] = t;      // never true: keeps the chains alive
+}
+
+cudaError_t launch_fp64_peak(int iters, int n_sms, double* sink, cudaStream_t s) {
+  fp64_peak_kernel<<<n_sms * 8, 256, 0, s>>>(iters, 1.0, sink);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------- launchers
 int geometry_grid(int64_t n, int n_sms) {
   const int64_t blocks = (n + 255) / 256;

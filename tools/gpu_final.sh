@@ -8,7 +8,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "py
 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
-SMALL="python bench.py --steps 2 --warmup 3 --images 24 --no-cpu-baseline"
+SMALL="python bench.py --steps 2 --warmup 3 --images 24 --no-cpu-baseline --no-extras"
 $SMALL > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $SMALL > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
