@@ -215,6 +215,13 @@ SFM_API int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const do
                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
                             double* resid, double* jac, int iters, float* ms_per_launch);
 
+/* estimate_normals(pts3d, K, normals) (NViewReconstuct.cpp:551-599, called with K = 10 at
+ * :1502) with PCAFitPlane (:601-690): per point the K nearest OTHER points (brute force), the
+ * eigenvector of smallest eigenvalue of their covariance, oriented so that normal . centroid <= 0
+ * and normalised.  pts and normals are [n_pts][3] doubles (std::vector<cv::Point3d>).
+ * 3 <= K <= 16, n_pts > K. */
+SFM_API int sfm_estimate_normals(sfm_ctx* ctx, const double* pts, int64_t n_pts, int K, double* normals);
+
 /* ---- output files: save_structure() / write_ply_binary() ---------------------------- */
 
 /* Writes the file save_structure() writes (NViewReconstuct.cpp:186-227) byte for byte as

@@ -191,6 +191,32 @@ def reproject_jacobians(intr, ext, pts, cam_idx, pt_idx) -> np.ndarray:
     return J
 
 
+def estimate_normals(pts3d, K: int = 10) -> np.ndarray:
+    """estimate_normals (NViewReconstuct.cpp:551-599) + PCAFitPlane (:601-690): K nearest other
+    points (brute force), covariance of the neighbours about their mean, eigenvector of the
+    smallest eigenvalue, flipped when normal . centroid > 0 (:672-677), normalised.
+    Pinned against the reference's own bundled output: the normals stored in
+    Viewer/structure_ba.ply are reproduced from the points of Viewer/structure_ba.yml with zero
+    float32 error (tests/test_oracle_geometry.py)."""
+    X = np.asarray(pts3d, np.float64).reshape(-1, 3)
+    n = X.shape[0]
+    out = np.empty_like(X)
+    for r0 in range(0, n, 1024):
+        d = X[r0:r0 + 1024, None, :] - X[None, :, :]
+        d2 = (d[:, :, 0] * d[:, :, 0] + d[:, :, 1] * d[:, :, 1]) + d[:, :, 2] * d[:, :, 2]
+        d2[np.arange(d2.shape[0]), np.arange(r0, r0 + d2.shape[0])] = np.inf
+        idx = np.argsort(d2, 1, kind="stable")[:, :K]
+        nb = X[idx]
+        mean = nb.mean(1)
+        c = nb - mean[:, None, :]
+        A = np.einsum("nki,nkj->nij", c, c) / K
+        _, V = np.linalg.eigh(A)
+        nrm = V[:, :, 0].copy()
+        nrm[(nrm * mean).sum(1) > 0] *= -1
+        out[r0:r0 + 1024] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    return out
+
+
 def huber_cost(resid: np.ndarray, delta: float = 4.0) -> float:
     """0.5 * sum rho(s), s = |r|^2, ceres::HuberLoss(delta): rho = s (s <= delta^2),
     2*delta*sqrt(s) - delta^2 otherwise (NViewReconstuct.cpp:1184)."""

@@ -37,6 +37,7 @@ SYMBOLS = {
     "sfm_upload_descriptors_bin": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_reproject_jacobians": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _pd, _pd, _i, _pf]),
     "sfm_probe_fp64_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),
+    "sfm_estimate_normals": (_i, [_vp, _pd, _i64, _i, _pd]),
     "sfm_upload_keypoints": (_i, [_vp, _i, C.POINTER(_vp), _pi]),
     "sfm_get_matched_points": (_i, [_vp, _i, C.POINTER(C.c_uint8), _pf, _pf, _i64, _pi64]),
     "sfm_reconstruct_pair": (_i, [_vp, _i, _pd, _pd, _pd, _pd, _pd, C.POINTER(C.c_uint8), _pd, _i64, _pi64]),

@@ -289,6 +289,15 @@ class Context:
             _ptr(jac, C.c_double) if n_obs else None, iters, C.byref(ms)))
         return (resid, jac, ms.value) if iters > 0 else (resid, jac)
 
+    def estimate_normals(self, pts3d, K: int = 10):
+        """estimate_normals(pts3d, K, normals), NViewReconstuct.cpp:551-599 (K = 10 at :1502):
+        returns normals [N,3] float64."""
+        pts = np.ascontiguousarray(pts3d, np.float64).reshape(-1, 3)
+        out = np.empty_like(pts)
+        self._check(self._lib.sfm_estimate_normals(self._h, _ptr(pts, C.c_double), pts.shape[0], K,
+                                                   _ptr(out, C.c_double)))
+        return out
+
     # ------------------------------------------------------------------ timing hooks
     def timer_start(self):
         self._check(self._lib.sfm_timer_start(self._h))

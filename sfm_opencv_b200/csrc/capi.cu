@@ -45,6 +45,7 @@ cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int
 cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32_t* sel, int64_t n,
                                          const float* kp_q, const float* kp_t, float* xy,
                                          cudaStream_t s);
+cudaError_t launch_normals(const double* pts, int n, int K, double* normals, cudaStream_t s);
 cudaError_t launch_fp64_peak(int iters, int n_sms, double* sink, cudaStream_t s);
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
 cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam, double* cam,
@@ -636,6 +637,24 @@ int sfm_triangulate_batch_timed(sfm_ctx* ctx, const float* P, const float* xy, i
                                 float* ms_per_launch) {
   if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
   return triangulate_common(ctx, P, xy, n_views, n_pts, X4, xyz, iters, ms_per_launch);
+}
+
+// ----------------------------------------------------------------------------- normals
+int sfm_estimate_normals(sfm_ctx* ctx, const double* pts, int64_t n_pts, int K, double* normals) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!pts || !normals) return fail(ctx, SFM_E_INVALID, "null points / normals");
+  if (K < 3 || K > 16) return fail(ctx, SFM_E_INVALID, "K must be in 3..16 (reference: 10)");
+  if (n_pts <= K || n_pts > (1ll << 30))
+    return fail(ctx, SFM_E_INVALID, "need more than K points (the reference pops K neighbours from a heap of n-1)");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->gpts.ensure(sizeof(double) * 3 * static_cast<size_t>(n_pts)));
+  CK(ctx->gres.ensure(sizeof(double) * 3 * static_cast<size_t>(n_pts)));
+  CK(cudaMemcpyAsync(ctx->gpts.p, pts, sizeof(double) * 3 * static_cast<size_t>(n_pts), cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_normals(ctx->gpts.as<double>(), static_cast<int>(n_pts), K, ctx->gres.as<double>(), ctx->stream));
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(normals, ctx->gres.p, sizeof(double) * 3 * static_cast<size_t>(n_pts), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SFM_OK;
 }
 
 // ----------------------------------------------------------------------------- Jacobians

@@ -390,6 +390,125 @@ cost_sum_kernel(const double* __restrict__ block_cost, int n, double* __restrict
   if (threadIdx.x == 0) *out = 0.5 * s[0];
 }
 
+// ---------------------------------------------------------------------------------------
+// estimate_normals (NViewReconstuct.cpp:551-599) + PCAFitPlane (:601-690): for every point the
+// K nearest other points (brute force, fp64 distances as the reference's Pt3dDist compares them),
+// the covariance of those K neighbours about their own mean, its eigenvector of smallest
+// eigenvalue, flipped so that normal . centroid <= 0 (towards the camera at the origin, :672-677)
+// and normalised.  One thread per point; candidates stream through shared memory in tiles; the
+// running top-K is a sorted register array (insertion only when a candidate beats the K-th).
+constexpr int kNrmThreads = 128;
+constexpr int kNrmTile = 256;
+constexpr int kNrmKMax = 16;
+
+__device__ __forceinline__ void jacobi_rotate(double (&A)[3][3], double (&V)[3][3], int p, int q) {
+  if (fabs(A[p][q]) < 1e-300) return;
+  const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {                       // A <- A J
+    const double akp = A[k][p], akq = A[k][q];
+    A[k][p] = c * akp - s * akq;
+    A[k][q] = s * akp + c * akq;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {                       // A <- J^T A
+    const double apk = A[p][k], aqk = A[q][k];
+    A[p][k] = c * apk - s * aqk;
+    A[q][k] = s * apk + c * aqk;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {                       // V <- V J
+    const double vkp = V[k][p], vkq = V[k][q];
+    V[k][p] = c * vkp - s * vkq;
+    V[k][q] = s * vkp + c * vkq;
+  }
+}
+
+__global__ void __launch_bounds__(kNrmThreads)
+normals_kernel(const double* __restrict__ pts, int n, int K, double* __restrict__ normals) {
+  __shared__ double s_p[kNrmTile][3];
+  const int i = blockIdx.x * kNrmThreads + threadIdx.x;
+  const int ic = min(i, n - 1);
+  const double px = pts[3 * ic], py = pts[3 * ic + 1], pz = pts[3 * ic + 2];
+  double bd[kNrmKMax];
+  int bi[kNrmKMax];
+#pragma unroll
+  for (int k = 0; k < kNrmKMax; ++k) { bd[k] = DBL_MAX; bi[k] = -1; }
+  double worst = DBL_MAX;                              // current K-th smallest distance^2
+  for (int j0 = 0; j0 < n; j0 += kNrmTile) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kNrmTile * 3; e += kNrmThreads)
+      if (j0 * 3 + e < n * 3) (&s_p[0][0])[e] = pts[static_cast<size_t>(j0) * 3 + e];
+    __syncthreads();
+    const int m = min(kNrmTile, n - j0);
+    for (int r = 0; r < m; ++r) {
+      const double dx = px - s_p[r][0], dy = py - s_p[r][1], dz = pz - s_p[r][2];
+      // (dx*dx + dy*dy) + dz*dz without contraction: the reference's expression order (:470-472)
+      const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      if (d < worst && j0 + r != ic) {
+        // sorted insertion; entries beyond K-1 are never read
+        double cd = d;
+        int ci = j0 + r;
+#pragma unroll
+        for (int k = 0; k < kNrmKMax; ++k) {
+          if (k < K && cd < bd[k]) {
+            const double td = bd[k]; const int ti = bi[k];
+            bd[k] = cd; bi[k] = ci;
+            cd = td; ci = ti;
+          }
+        }
+        worst = DBL_MAX;
+#pragma unroll
+        for (int k = 0; k < kNrmKMax; ++k)
+          if (k == K - 1) worst = bd[k];
+      }
+    }
+  }
+  if (i >= n) return;
+  // PCAFitPlane: mean and covariance of the K neighbours (the point itself is not included)
+  double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll
+  for (int k = 0; k < kNrmKMax; ++k)
+    if (k < K) { mx += pts[3 * bi[k]]; my += pts[3 * bi[k] + 1]; mz += pts[3 * bi[k] + 2]; }
+  const double inv = 1.0 / static_cast<double>(K);
+  mx *= inv; my *= inv; mz *= inv;
+  double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int k = 0; k < kNrmKMax; ++k)
+    if (k < K) {
+      const double x = pts[3 * bi[k]] - mx, y = pts[3 * bi[k] + 1] - my, z = pts[3 * bi[k] + 2] - mz;
+      A[0][0] += x * x; A[1][1] += y * y; A[2][2] += z * z;
+      A[0][1] += x * y; A[0][2] += x * z; A[1][2] += y * z;
+    }
+  A[0][0] *= inv; A[1][1] *= inv; A[2][2] *= inv;
+  A[0][1] *= inv; A[0][2] *= inv; A[1][2] *= inv;
+  A[1][0] = A[0][1]; A[2][0] = A[0][2]; A[2][1] = A[1][2];
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 12; ++sweep) {           // cyclic Jacobi: quadratic convergence
+    jacobi_rotate(A, V, 0, 1);
+    jacobi_rotate(A, V, 0, 2);
+    jacobi_rotate(A, V, 1, 2);
+  }
+  int mn = 0;
+  if (A[1][1] < A[mn][mn]) mn = 1;
+  if (A[2][2] < A[mn][mn]) mn = 2;
+  double a = mn == 0 ? V[0][0] : (mn == 1 ? V[0][1] : V[0][2]);
+  double b = mn == 0 ? V[1][0] : (mn == 1 ? V[1][1] : V[1][2]);
+  double c = mn == 0 ? V[2][0] : (mn == 1 ? V[2][1] : V[2][2]);
+  if (a * mx + b * my + c * mz > 0.0) { a = -a; b = -b; c = -c; }     // :672-677
+  const double den = sqrt(a * a + b * b + c * c);
+  normals[3 * i] = a / den;
+  normals[3 * i + 1] = b / den;
+  normals[3 * i + 2] = c / den;
+}
+
+cudaError_t launch_normals(const double* pts, int n, int K, double* normals, cudaStream_t s) {
+  normals_kernel<<<(n + kNrmThreads - 1) / kNrmThreads, kNrmThreads, 0, s>>>(pts, n, K, normals);
+  return cudaGetLastError();
+}
+
 // Bare fp64 issue-rate probe: 8 independent DFMA chains per thread, registers only.  The
 // triangulation kernel is bound by this pipe, not by HBM.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {

@@ -200,3 +200,35 @@ def test_jacobians_single_observation_and_timed(ctx):
     cam = np.repeat(np.arange(2), 10).astype(np.int32); pt = np.tile(np.arange(10), 2).astype(np.int32)
     r2, J2, ms = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt, sc["xy"].reshape(-1, 2), iters=3)
     assert ms > 0 and np.allclose(J2, G.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt), rtol=1e-10, atol=1e-12)
+
+
+def test_normals_reproduce_the_bundled_ply(ctx):
+    """sfm_estimate_normals on the points of the reference's bundled structure_ba.yml must give
+    the normals stored in its bundled structure_ba.ply (float32)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "viewer_outputs.npz"))
+    X, v = g["structure_ba_yml_X"], g["structure_ba_ply_v"]
+    n = ctx.estimate_normals(X, 10)
+    assert n.shape == X.shape and np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-12)
+    assert np.abs(n.astype(np.float32) - v[:, 3:]).max() <= 1e-6
+    assert np.abs(n - G.estimate_normals(X, 10)).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,K", [(11, 10), (300, 3), (1000, 16), (4097, 10)])
+def test_normals_vs_oracle(ctx, n, K):
+    rng = np.random.default_rng(n + K)
+    # points near a wavy surface in front of the camera: well-defined tangent planes
+    u = rng.uniform(-3, 3, (n, 2))
+    X = np.stack([u[:, 0], u[:, 1], 8 + 0.3 * np.sin(u[:, 0]) + 0.2 * np.cos(2 * u[:, 1]) + rng.normal(0, 0.01, n)], 1)
+    got = ctx.estimate_normals(X, K)
+    ref = G.estimate_normals(X, K)
+    assert np.abs(got - ref).max() < 1e-7
+    assert ((got * X).sum(1) < 0).mean() > 0.99           # oriented towards the camera
+
+
+def test_normals_errors(ctx):
+    import sfm_opencv_b200 as sfm
+    with pytest.raises(sfm.SfmError):
+        ctx.estimate_normals(np.zeros((10, 3)), 10)       # needs more than K points
+    with pytest.raises(sfm.SfmError):
+        ctx.estimate_normals(np.zeros((100, 3)), 40)

@@ -124,3 +124,14 @@ def test_jacobian_oracle_vs_central_differences():
     for q in range(3):
         e = np.zeros(3); e[q] = 1.0
         assert np.allclose(J[~big][:, :, 4 + q], np.einsum("nij,nj->ni", A, np.cross(e, Xs)), rtol=1e-12, atol=1e-12)
+
+
+def test_normals_oracle_reproduces_the_bundled_ply():
+    """The reference's own output: normals of Viewer/structure_ba.ply (float32) were computed by
+    estimate_normals(pts3d, 10) from the points saved in Viewer/structure_ba.yml (:1502-1511)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "viewer_outputs.npz"))
+    X, v = g["structure_ba_yml_X"], g["structure_ba_ply_v"]
+    assert np.array_equal(X.astype(np.float32), v[:, :3])
+    n = G.estimate_normals(X, 10)
+    assert np.abs(n.astype(np.float32) - v[:, 3:]).max() <= 1e-6
