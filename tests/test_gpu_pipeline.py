@@ -80,11 +80,45 @@ def test_later_pairs_use_all_matches(ctx, desktop):
         assert G.point_rel_err(xyz[inl], ref[inl]).max() < REL_TOL
 
 
+def test_first_pair_reproduces_the_bundled_structure_yml(ctx, golden):
+    """End to end against the reference's OWN bundled output (live configuration): AKAZE
+    descriptors of desktop 0/1 -> NORM_HAMMING2 matching on the GPU (2186 matches) -> device-side
+    get_matched_points -> findEssentialMat / recoverPose (cv2 on the host, as the reference; fresh
+    default RNG) -> maskout + reconstruct on the GPU.  Viewer/structure.yml holds camera 1's pose
+    and, as its first 1847 points, exactly this structure (init_structure, :916-987)."""
+    import os
+    import cv2
+    g = golden("desktop", "akaze")
+    v = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "viewer_outputs.npz"))
+    K = G.K_REFERENCE
+    ctx.upload_descriptors([g["desc_0"], g["desc_1"]], norm="hamming2")
+    ctx.upload_keypoints([g["kp_0"], g["kp_1"]])
+    m, _, _ = ctx.match_pairs([(0, 1)])
+    assert len(m[0]) == 2186
+    p1, p2 = ctx.get_matched_points(0, len(m[0]))
+    focal, pp = 0.5 * (K[0, 0] + K[1, 1]), (K[0, 2], K[1, 2])
+    cv2.setRNGSeed(0)                                  # state of a fresh process
+    E, mask = cv2.findEssentialMat(p1, p2, focal, pp, cv2.RANSAC, 0.999, 1.0)
+    _, R, T, mask = cv2.recoverPose(E, p1, p2, focal=focal, pp=pp, mask=mask)
+    mask = mask.reshape(-1)
+    if int((mask > 0).sum()) != 1847 or np.abs(R - v["structure_yml_R"][1]).max() > 1e-9:
+        pytest.skip("cv2 RANSAC did not land on the bundled pose (RNG / version dependent)")
+    assert np.abs(T.reshape(-1) - v["structure_yml_T"][1].reshape(-1)).max() < 1e-9
+    xyz = ctx.reconstruct_pair(0, len(m[0]), K, np.eye(3), np.zeros(3), R, T, mask)
+    want = v["structure_yml_X"][:1847]
+    assert xyz.shape == want.shape
+    assert G.point_rel_err(xyz, want).max() < 2e-5      # bundled file: OpenCV 4.4 on another platform
+
+
 def test_errors(ctx, desktop):
     import sfm_opencv_b200 as sfm
     from sfm_opencv_b200 import _capi
-    g, kps, m = desktop
+    g, kps, _ = desktop
     K = G.K_REFERENCE
+    n = int(g["n_img"])                                # the session context is shared: set it up again
+    ctx.upload_descriptors([g[f"desc_{i}"] for i in range(n)])
+    ctx.upload_keypoints(kps)
+    m, _, _ = ctx.match_pairs(M.consecutive_pairs(n))
     with pytest.raises(sfm.SfmError) as e:
         ctx.reconstruct_pair(0, len(m[0]), K, np.eye(3), np.zeros(3), np.eye(3), np.ones(3),
                              np.zeros(len(m[0]), np.uint8))
