@@ -44,7 +44,10 @@
 
 namespace sfm {
 
-constexpr int kStages = 6;                      // B-tile ring depth (16 KB each)
+#ifndef SFM_STAGES
+#define SFM_STAGES 6                            // tools/variants.py builds other depths with -D
+#endif
+constexpr int kStages = SFM_STAGES;             // B-tile ring depth (16 KB each)
 constexpr int kAccBufs = 2;                     // TMEM accumulator buffers (2 x 128 columns each)
 constexpr int kFirstMmaWarp = 4;                // warps 1..3 idle (warpgroup granularity)
 constexpr int kMmaWarps = 4;                    // (query half, tile parity)
@@ -159,7 +162,15 @@ __device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
 
 // exact keys of the 8 columns of a group (column keys from the shared-memory ring) -> (m1, m2)
 __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr, RowTop2& s) {
+#ifdef SFM_EXP_NOLDS   // timing experiment (results invalid): column keys without the LDS latency
+  const int4 c0 = make_int4(ck_addr, ck_addr + 1, ck_addr + 2, ck_addr + 3);
+  const int4 c1 = make_int4(ck_addr + 4, ck_addr + 5, ck_addr + 6, ck_addr + 7);
+#else
+#ifdef SFM_EXP_XLAT    // timing experiment: one more dependent shared-memory round trip per hit
+  ck_addr += static_cast<uint32_t>(lds_32(ck_addr)) & 0u;
+#endif
   const int4 c0 = lds_v4(ck_addr), c1 = lds_v4(ck_addr + 16);
+#endif
   int k[8];
   k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
   k[2] = make_key(a[2], c0.z); k[3] = make_key(a[3], c0.w);
@@ -195,11 +206,29 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+#ifdef SFM_EXP_XFAST   // timing experiment: 4 more independent ALU ops per chunk in the fast path
+    {
+      int x0 = s.g1i, x1 = s.g2i, x2 = s.g1i, x3 = s.g2i;
+      asm volatile("max.s32 %0, %0, %4;\n\tmax.s32 %1, %1, %5;\n\tmax.s32 %2, %2, %6;\n\tmax.s32 %3, %3, %7;"
+                   : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3) : "r"(n8[0]), "r"(n8[1]), "r"(n8[2]), "r"(n8[3]));
+      if ((x0 ^ x1 ^ x2 ^ x3) == 0x12345677) s.g1i = x0;
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (h[j]) {
         group_insert(&r[8 * j], ck_addr + 32 * j, s);
+#ifndef SFM_EXP_NOBV
         s.bv = min(s.bv, s.m2 >> kColBits);
+#endif
+#ifdef SFM_EXP_XALU    // timing experiment: 8 more dependent ALU ops per hit (no effect on values)
+        {
+          int x = s.bv;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) asm volatile("max.s32 %0, %0, %1;" : "+r"(x) : "r"(s.bv - q - 1));
+          s.bv = x;
+        }
+#endif
       }
     }
   }
