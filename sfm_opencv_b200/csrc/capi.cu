@@ -363,10 +363,10 @@ int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* des
 // Binary descriptors for NORM_HAMMING2 (the live AKAZE path, NViewReconstuct.cpp:797,876).
 int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
                                const int32_t* n_desc, int bytes) {
-  constexpr int kBinRowPad = 128, kBinRowBytes = 64;
+  constexpr int kBinRowPad = 128, kBinRowBytes = 128, kBinMaxBytes = 64;   // rows are stored expanded
   if (!ctx) return SFM_E_INVALID;
   if (n_img <= 0 || !desc_u8 || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
-  if (bytes <= 0 || bytes > kBinRowBytes)
+  if (bytes <= 0 || bytes > kBinMaxBytes)
     return fail(ctx, SFM_E_DIM, "binary descriptors must be 1..64 bytes (AKAZE: 61)");
   CK(cudaSetDevice(ctx->device));
   ctx->bank_ready = false;

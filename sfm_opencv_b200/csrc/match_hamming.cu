@@ -6,10 +6,17 @@
 // counts the 2-bit cells in which a and b differ: per byte popcount((x | x >> 1) & 0x55),
 // x = a ^ b.  Results are ordered by (distance, lower train index first).
 //
-// This is integer / bit work for the CUDA cores (XOR, shift, LOP3, POPC), not a tensor-core
-// shape: 16 words per descriptor pair, ~4.3 instructions per word.
-//   * bank: every descriptor is one 64-byte row (bytes beyond the descriptor length are zero
-//     and add nothing to a distance), images padded to kBinRowPad rows;
+// This is integer / bit work for the CUDA cores (LOP3, POPC), not a tensor-core shape.
+//   * bank: every descriptor (<= 64 bytes, zero padded: zero bytes add nothing to a distance)
+//     is stored EXPANDED to 128 bytes so that the inner loop needs no shifts and no masks.
+//     With m = 0x55555555 and x = a ^ b, the cell flags of a word are
+//         (x | x >> 1) & m  =  ((a & m) ^ (b & m)) | (((a >> 1) & m) ^ ((b >> 1) & m)),
+//     i.e. two 3-input LOP3 on pre-masked operands.  Odd words use the mirrored form on the
+//     odd bit positions, (a & ~m, (a << 1) & ~m), so that the flags of an (even, odd) word pair
+//     interleave in one register and share one POPC: 4 LOP3 + 1 POPC per two words, 2.75
+//     instructions per word instead of 4.3.  Row layout: word w of the descriptor becomes the
+//     pair (E[2w], E[2w+1]) = (a & m, (a >> 1) & m) for even w, (a & ~m, (a << 1) & ~m) for odd w;
+//     images are padded to kBinRowPad rows;
 //   * hamming2_knn_kernel: a block = 128 query rows (one per thread, descriptor in registers)
 //     x one split of the train image; train rows stream through shared memory in 64-row tiles
 //     (cp.async double buffer) and are read as warp-wide broadcasts; a thread keeps its exact
@@ -25,19 +32,27 @@
 
 namespace sfm {
 
-constexpr int kBinWords = 16;        // 64-byte rows
+constexpr int kBinWords = 32;        // 128-byte expanded rows (16 descriptor words x 2)
 constexpr int kBinQRows = 128;       // query rows per block (one per thread)
 constexpr int kBinTile = 64;         // train rows per shared-memory tile
 constexpr int kBinIdxBits = 20;      // packed key = distance << 20 | train index
 
-// Copies n descriptors of `bytes` bytes each into 64-byte bank rows (tail bytes stay zero:
-// the bank is memset before).
+// Expands n descriptors of `bytes` bytes each into 128-byte bank rows (see the header comment);
+// one thread per descriptor word, bytes beyond the descriptor read as zero.
 __global__ void bin_pack_kernel(const uint8_t* __restrict__ src, int n, int bytes, int row0,
                                 uint8_t* __restrict__ bank) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<int64_t>(n) * bytes) return;
-  const int r = static_cast<int>(i / bytes), b = static_cast<int>(i % bytes);
-  bank[static_cast<size_t>(row0 + r) * 64 + b] = src[i];
+  if (i >= static_cast<int64_t>(n) * 16) return;
+  const int r = static_cast<int>(i >> 4), w = static_cast<int>(i & 15);
+  uint32_t a = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (4 * w + b < bytes) a |= static_cast<uint32_t>(src[static_cast<size_t>(r) * bytes + 4 * w + b]) << (8 * b);
+  constexpr uint32_t m = 0x55555555u;
+  uint2 e;
+  if ((w & 1) == 0) e = make_uint2(a & m, (a >> 1) & m);
+  else e = make_uint2(a & ~m, (a << 1) & ~m);
+  reinterpret_cast<uint2*>(bank + static_cast<size_t>(row0 + r) * 128)[w] = e;
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -49,18 +64,18 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// NORM_HAMMING2 distance of two 64-byte rows.  Two words share one POPC: the cell flags of an
-// even word sit on even bit positions, those of the following odd word on odd positions.
+// NORM_HAMMING2 distance of two expanded rows: per descriptor word pair 4 LOP3 + 1 POPC.
 __device__ __forceinline__ int hamming2_row(const uint32_t (&q)[kBinWords], const uint4* t4) {
   int d = 0;
 #pragma unroll
   for (int v = 0; v < kBinWords / 4; ++v) {
+    // t = (even word: b & m, (b >> 1) & m | odd word: b & ~m, (b << 1) & ~m)
     const uint4 t = t4[v];
-    const uint32_t x0 = q[4 * v + 0] ^ t.x, x1 = q[4 * v + 1] ^ t.y;
-    const uint32_t x2 = q[4 * v + 2] ^ t.z, x3 = q[4 * v + 3] ^ t.w;
-    const uint32_t c01 = ((x0 | (x0 >> 1)) & 0x55555555u) | ((x1 | (x1 << 1)) & 0xAAAAAAAAu);
-    const uint32_t c23 = ((x2 | (x2 >> 1)) & 0x55555555u) | ((x3 | (x3 << 1)) & 0xAAAAAAAAu);
-    d += __popc(c01) + __popc(c23);
+    uint32_t c = q[4 * v + 0] ^ t.x;               // flags of the even word, even positions
+    c |= q[4 * v + 1] ^ t.y;
+    c |= q[4 * v + 2] ^ t.z;                       // flags of the odd word, odd positions
+    c |= q[4 * v + 3] ^ t.w;
+    d += __popc(c);
   }
   return d;
 }
@@ -69,7 +84,7 @@ __device__ __forceinline__ int hamming2_row(const uint32_t (&q)[kBinWords], cons
 __global__ void __launch_bounds__(kBinQRows)
 hamming2_knn_kernel(const uint8_t* __restrict__ bank, const PairDesc* __restrict__ pairs,
                     const int2* __restrict__ items, int n_splits, int2* __restrict__ partial) {
-  __shared__ __align__(16) uint4 s_t[2][kBinTile * (kBinWords / 4)];
+  __shared__ __align__(16) uint4 s_t[2][kBinTile * (kBinWords / 4)];   // 2 x 8 KB tiles
   const int2 it = items[blockIdx.x];
   const PairDesc pd = pairs[it.x];
   const int split = blockIdx.y;
@@ -83,7 +98,7 @@ hamming2_knn_kernel(const uint8_t* __restrict__ bank, const PairDesc* __restrict
   uint32_t q[kBinWords];
   {
     const int qr = min(row, pd.nq - 1);                      // clamp: padding threads still help load
-    const uint4* src = reinterpret_cast<const uint4*>(bank + static_cast<size_t>(pd.q_row0 + qr) * 64);
+    const uint4* src = reinterpret_cast<const uint4*>(bank + static_cast<size_t>(pd.q_row0 + qr) * 128);
 #pragma unroll
     for (int v = 0; v < kBinWords / 4; ++v) {
       const uint4 w = __ldg(src + v);
@@ -91,15 +106,15 @@ hamming2_knn_kernel(const uint8_t* __restrict__ bank, const PairDesc* __restrict
     }
   }
   int m1 = INT32_MAX, m2 = INT32_MAX;
-  const uint8_t* tbase = bank + static_cast<size_t>(pd.t_row0) * 64;
+  const uint8_t* tbase = bank + static_cast<size_t>(pd.t_row0) * 128;
   auto load_tile = [&](int buf, int r0) {
-    // 64 rows x 64 B = 256 x 16 B: two 16-byte pieces per thread; rows past the image are
+    // 64 rows x 128 B = 512 x 16 B: four 16-byte pieces per thread; rows past the image are
     // padding rows of the bank (readable) and are never scored
     const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(&s_t[buf][0]));
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const int piece = threadIdx.x + k * kBinQRows;
-      cp_async16(dst + piece * 16, tbase + static_cast<size_t>(r0) * 64 + piece * 16);
+      cp_async16(dst + piece * 16, tbase + static_cast<size_t>(r0) * 128 + piece * 16);
     }
     cp_async_commit();
   };
@@ -163,7 +178,7 @@ __global__ void hamming2_merge_kernel(const int2* __restrict__ partial, int64_t 
 // ------------------------------------------------------------------------------- launchers
 cudaError_t launch_bin_pack(const uint8_t* src, int n, int bytes, int row0, uint8_t* bank,
                             cudaStream_t s) {
-  const int64_t tot = static_cast<int64_t>(n) * bytes;
+  const int64_t tot = static_cast<int64_t>(n) * 16;
   if (tot > 0)
     bin_pack_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(src, n, bytes, row0, bank);
   return cudaGetLastError();

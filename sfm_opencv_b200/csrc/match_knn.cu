@@ -203,9 +203,14 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
     const int4 nn = lds_v4(gm_addr);
     const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
     bool h[4];
+#ifdef SFM_EXP_NOVOTE   // rows that pass branch to the insert on their own (no warp vote)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
+#else
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+#endif
 #ifdef SFM_EXP_XFAST   // timing experiment: 4 more independent ALU ops per chunk in the fast path
     {
       int x0 = s.g1i, x1 = s.g2i, x2 = s.g1i, x3 = s.g2i;
