@@ -23,4 +23,10 @@ echo "ncu tri rc=$?"
 $GEO > gpurun_out/${TAG}_plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:residual_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_res $GEO > gpurun_out/${TAG}_ncu4.log 2>&1
 echo "ncu res rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:jacobian_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_jac $GEO > gpurun_out/${TAG}_ncu5.log 2>&1
+echo "ncu jac rc=$?"
+HAM="python tools/exp_hamming.py"
+$HAM > gpurun_out/${TAG}_hamming.json 2> gpurun_out/${TAG}_hamming.err &&
+ncu --set full --clock-control none --import-source on -k regex:hamming2_knn_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_ham $HAM > gpurun_out/${TAG}_ncu6.log 2>&1
+echo "ncu hamming rc=$?"
 ls -la gpurun_out | grep ${TAG}
