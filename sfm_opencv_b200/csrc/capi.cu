@@ -95,6 +95,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct sfm_ctx {
   int device = 0;
   int n_sms = 0;
+  size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[2] = {nullptr, nullptr};   // sfm_timer_start / sfm_timer_stop
@@ -108,9 +109,10 @@ struct sfm_ctx {
   std::vector<int32_t> img_min_norm;
   std::vector<int32_t> img_n, img_row0;
   std::vector<int2> h_items;                   // reused host staging of the work-item table
+  std::vector<int32_t> h_order;                // processing order of the pairs (L2 blocking)
   int64_t bank_rows = 0;
   bool bank_ready = false;
-  bool bank_binary = false;   // false: u8 x 128 (NORM_L2); true: 64-byte rows (NORM_HAMMING2)
+  bool bank_binary = false;   // false: u8 x 128 (NORM_L2); true: 128-byte expanded rows (NORM_HAMMING2)
   DevBuf partial;             // NORM_HAMMING2: per-split top-2 of every query row
   CUtensorMap tmap;   // u8 bank, box = 128 rows x 128 bytes, 128-byte swizzle
 
@@ -195,6 +197,7 @@ sfm_ctx* sfm_create(int device_id, int* err) {
   sfm_ctx* ctx = new sfm_ctx();
   ctx->device = device_id;
   ctx->n_sms = prop.multiProcessorCount;
+  ctx->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return bail(SFM_E_CUDA, "cudaStreamCreate failed");
@@ -421,6 +424,7 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   std::vector<int2>& items = ctx->h_items;    // work items: (pair, 256-row query block)
   items.clear();
   int64_t rows = 0;
+  int32_t max_n = 1;
   for (int p = 0; p < n_pairs; ++p) {
     const int q = pair_q[p], t = pair_t[p];
     if (q < 0 || q >= n_img || t < 0 || t >= n_img)
@@ -435,12 +439,34 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     pd.nt = ctx->img_n[t];
     pd.nt_min = ctx->img_min_norm[t];
     pd.pad = 0;
-    pd.knn_off = rows;
+    pd.knn_off = rows;                          // results stay in caller order
     rows += pd.nq;
+    max_n = std::max(max_n, std::max(pd.nq, pd.nt));
+  }
+  // Processing order (results are placed by knn_off, so it is free): pairs are visited in
+  // blocks of B x B (query image, train image) so that the 2 B descriptor sets a block
+  // touches stay in L2 -- an exhaustive pair list otherwise streams every train image from
+  // HBM once per query image (measured: 34 GB per launch for a 210 MB bank).
+  {
+    const size_t img_bytes = static_cast<size_t>(max_n) * 128;
+    const int B = static_cast<int>(std::max<size_t>(1, ctx->l2_bytes * 6 / 10 / (2 * img_bytes)));
+    std::vector<int32_t>& order = ctx->h_order;
+    order.resize(n_pairs);
+    for (int p = 0; p < n_pairs; ++p) order[p] = p;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      const int qa = pair_q[a] / B, qb = pair_q[b] / B, ta = pair_t[a] / B, tb = pair_t[b] / B;
+      if (qa != qb) return qa < qb;
+      if (ta != tb) return ta < tb;
+      if (pair_q[a] != pair_q[b]) return pair_q[a] < pair_q[b];
+      if (pair_t[a] != pair_t[b]) return pair_t[a] < pair_t[b];
+      return a < b;
+    });
     const int qblock = ctx->bank_binary ? 128 : kTileM;   // query rows per work item
-    const int mb = (pd.nq + qblock - 1) / qblock;
-    for (int m = 0; m < mb; ++m) items.push_back(make_int2(p, m));
-    if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many query blocks");
+    for (int32_t p : order) {
+      const int mb = (pairs[p].nq + qblock - 1) / qblock;
+      for (int m = 0; m < mb; ++m) items.push_back(make_int2(p, m));
+      if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many query blocks");
+    }
   }
   const int64_t n_items = static_cast<int64_t>(items.size());
   *total_rows = rows;
