@@ -40,8 +40,8 @@ cudaError_t launch_hamming2_knn(const uint8_t* bank, const PairDesc* pairs, cons
                                 Knn2* knn, cudaStream_t s);
 // geometry.cu
 int geometry_grid(int64_t n, int n_sms);
-cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,
-                               float* X4, double* xyz, int n_sms, cudaStream_t s);
+cudaError_t launch_triangulate(const float* P, const float* P_host, const float* xy, int n_views,
+                               int64_t n_pts, float* X4, double* xyz, int n_sms, cudaStream_t s);
 cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32_t* sel, int64_t n,
                                          const float* kp_q, const float* kp_t, float* xy,
                                          cudaStream_t s);
@@ -627,13 +627,13 @@ static int triangulate_common(sfm_ctx* ctx, const float* P, const float* xy, int
   double* dxyz = (xyz || iters > 0) ? ctx->gxyz.as<double>() : nullptr;
   const int reps = iters > 0 ? iters : 1;
   if (iters > 0) {   // one untimed warm-up launch
-    CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
+    CK(launch_triangulate(ctx->gP.as<float>(), P, ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
                           ctx->n_sms, ctx->stream));
     ctx->launches += 1;
   }
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int r = 0; r < reps; ++r) {
-    CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
+    CK(launch_triangulate(ctx->gP.as<float>(), P, ctx->gxy.as<float>(), n_views, n_pts, dX4, dxyz,
                           ctx->n_sms, ctx->stream));
     ctx->launches += 1;
   }
@@ -866,7 +866,7 @@ int sfm_reconstruct_pair(sfm_ctx* ctx, int pair, const double K[9], const double
   CK(ctx->gP.ensure(sizeof P));
   CK(ctx->gxyz.ensure(sizeof(double) * 3 * static_cast<size_t>(n)));
   CK(cudaMemcpyAsync(ctx->gP.p, P, sizeof P, cudaMemcpyHostToDevice, ctx->stream));
-  CK(launch_triangulate(ctx->gP.as<float>(), ctx->gxy.as<float>(), 2, n, nullptr, ctx->gxyz.as<double>(),
+  CK(launch_triangulate(ctx->gP.as<float>(), P, ctx->gxy.as<float>(), 2, n, nullptr, ctx->gxyz.as<double>(),
                         ctx->n_sms, ctx->stream));
   ctx->launches += 1;
   CK(cudaMemcpyAsync(structure, ctx->gxyz.p, sizeof(double) * 3 * static_cast<size_t>(n), cudaMemcpyDeviceToHost,

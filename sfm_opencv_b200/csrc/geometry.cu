@@ -87,11 +87,20 @@ __device__ __forceinline__ double pow2_inv(double x) {
   return (e > 0 && e < 2046) ? __hiloint2double(ne << 20, 0) : 1.0;
 }
 
+// Projection matrices of up to kMaxViewsParam views travel as a kernel parameter: the fp64
+// FMAs then take them straight from the constant bank (no shared-memory loads, no registers).
+constexpr int kMaxViewsParam = 8;
+struct ProjParam {
+  double p[kMaxViewsParam * 12];
+};
+
+template <bool kParamP, int kV>     // kV > 0: view count known at compile time (the reference: 2)
 __global__ void __launch_bounds__(256)
-triangulate_kernel(const float* __restrict__ P, const float* __restrict__ xy, int n_views,
-                   int64_t n_pts, float* __restrict__ X4, double* __restrict__ xyz) {
-  __shared__ double sP[kMaxViewsSmem * 12];
-  const bool p_in_smem = n_views <= kMaxViewsSmem;
+triangulate_kernel(const __grid_constant__ ProjParam pp, const float* __restrict__ P,
+                   const float* __restrict__ xy, int n_views, int64_t n_pts,
+                   float* __restrict__ X4, double* __restrict__ xyz) {
+  __shared__ double sP[kParamP ? 1 : kMaxViewsSmem * 12];
+  const bool p_in_smem = !kParamP && n_views <= kMaxViewsSmem;
   if (p_in_smem) {
     for (int i = threadIdx.x; i < n_views * 12; i += blockDim.x) sP[i] = static_cast<double>(P[i]);
     __syncthreads();
@@ -100,12 +109,15 @@ triangulate_kernel(const float* __restrict__ P, const float* __restrict__ xy, in
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pts;
        i += stride) {
     Sym4 m = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int v = 0; v < n_views; ++v) {
+#pragma unroll
+    for (int v = 0; v < (kV > 0 ? kV : n_views); ++v) {
       const float2 p = __ldcs(reinterpret_cast<const float2*>(xy) + v * n_pts + i);
       const double x = p.x, y = p.y;
       double q[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) q[k] = p_in_smem ? sP[v * 12 + k] : static_cast<double>(P[v * 12 + k]);
+      for (int k = 0; k < 12; ++k)
+        q[k] = kParamP ? pp.p[v * 12 + k]
+                       : (p_in_smem ? sP[v * 12 + k] : static_cast<double>(P[v * 12 + k]));
       sym4_add_row(m, x * q[8] - q[0], x * q[9] - q[1], x * q[10] - q[2], x * q[11] - q[3]);
       sym4_add_row(m, y * q[8] - q[4], y * q[9] - q[5], y * q[10] - q[6], y * q[11] - q[7]);
     }
@@ -563,9 +575,18 @@ cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32
   return cudaGetLastError();
 }
 
-cudaError_t launch_triangulate(const float* P, const float* xy, int n_views, int64_t n_pts,
-                               float* X4, double* xyz, int n_sms, cudaStream_t s) {
-  triangulate_kernel<<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(P, xy, n_views, n_pts, X4, xyz);
+cudaError_t launch_triangulate(const float* P, const float* P_host, const float* xy, int n_views,
+                               int64_t n_pts, float* X4, double* xyz, int n_sms, cudaStream_t s) {
+  ProjParam pp;
+  if (P_host != nullptr && n_views <= kMaxViewsParam) {
+    for (int i = 0; i < n_views * 12; ++i) pp.p[i] = static_cast<double>(P_host[i]);
+    if (n_views == 2)
+      triangulate_kernel<true, 2><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
+    else
+      triangulate_kernel<true, 0><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
+  } else {
+    triangulate_kernel<false, 0><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
+  }
   return cudaGetLastError();
 }
 

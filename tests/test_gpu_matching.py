@@ -262,7 +262,7 @@ def test_sharded_contexts_equal_single(ctx):
 
 def _check_matches_only(ctx, bank, pairs, ratio=M.RATIO):
     ctx.upload_descriptors(bank)
-    m, md, knn = ctx.match_pairs(pairs, ratio=ratio)            # no raw kNN rows: match mode
+    m, md, knn = ctx.match_pairs(pairs, ratio=ratio)            # no raw kNN rows requested
     assert knn is None
     for p, (a, b) in enumerate(pairs):
         d, idx = M.knn2_int(bank[a], bank[b])
@@ -274,14 +274,14 @@ def _check_matches_only(ctx, bank, pairs, ratio=M.RATIO):
 
 
 @pytest.mark.parametrize("ratio", [0.6, 0.3, 0.8, 0.95, 0.99, 1.0, 1.5])
-def test_match_mode_ratios(ctx, ratio):
+def test_matches_only_ratios(ctx, ratio):
     bank = synth.image_bank(3, 1500, seed0=70)
     _check_matches_only(ctx, bank, [(0, 1), (1, 2), (0, 2), (2, 0)], ratio=ratio)
 
 
 @pytest.mark.parametrize("nq,nt", [(1, 2), (127, 255), (300, 2), (5, 1000), (1000, 5), (2048, 4100),
                                    (700, 9000)])
-def test_match_mode_ragged_and_duplicates(ctx, nq, nt):
+def test_matches_only_ragged_and_duplicates(ctx, nq, nt):
     q = synth.sift_like(nq, 300 + nq)
     t = synth.sift_like(nt, 400 + nt)
     k = min(nq, nt) // 3
@@ -292,7 +292,7 @@ def test_match_mode_ragged_and_duplicates(ctx, nq, nt):
     _check_matches_only(ctx, [q, t], [(0, 1)])
 
 
-def test_match_mode_near_threshold_rows(ctx):
+def test_matches_only_near_threshold_rows(ctx):
     """Rows whose d0 / d1 sits right at the ratio: the sure-fail margin must never flip one."""
     rng = np.random.default_rng(5)
     t = synth.sift_like(3000, 77)
@@ -308,7 +308,7 @@ def test_match_mode_near_threshold_rows(ctx):
 
 
 @pytest.mark.parametrize("name", ["crazyhorse", "desktop"])
-def test_match_mode_golden_datasets(ctx, golden, name):
+def test_matches_only_golden_datasets(ctx, golden, name):
     g = golden(name)
     n = int(g["n_img"])
     bank = [g[f"desc_{i}"] for i in range(n)]
@@ -321,7 +321,7 @@ def test_match_mode_golden_datasets(ctx, golden, name):
         assert _bits(md[p]) == _bits(g[f"min_dist_{p}"])
 
 
-def test_match_mode_equals_exact_mode_all_pairs(ctx):
+def test_matches_only_equals_knn_call_all_pairs(ctx):
     sizes = [700, 300, 1100, 64, 513, 2300]
     bank = [synth.sift_like(n, 140 + i) for i, n in enumerate(sizes)]
     for j in range(1, len(bank)):
@@ -330,8 +330,8 @@ def test_match_mode_equals_exact_mode_all_pairs(ctx):
         bank[j][:k] = np.clip(noisy, 0, 255).astype(np.uint8)
     pairs = M.all_pairs(len(bank)) + [(3, 0), (2, 2)]
     ctx.upload_descriptors(bank)
-    a, mda, _ = ctx.match_pairs(pairs)                       # match mode
-    b, mdb, _ = ctx.match_pairs(pairs, want_knn=True)        # exact top-2
+    a, mda, _ = ctx.match_pairs(pairs)
+    b, mdb, _ = ctx.match_pairs(pairs, want_knn=True)
     assert np.array_equal(mda.view(np.uint32), mdb.view(np.uint32))
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
