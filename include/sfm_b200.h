@@ -108,6 +108,15 @@ SFM_API int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* 
 SFM_API int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
                               const int32_t* n_desc, int dim);
 
+/* Asynchronous upload: returns as soon as the copies and pack kernels are queued on the
+ * context's copy stream.  desc[i] must stay valid (ideally pinned: sfm_host_alloc) until the next
+ * sfm_match_pairs* call returns; that call makes each of its kernels wait only for the images
+ * it reads, so matching overlaps the rest of the transfer, and it reports this upload's
+ * validation result (SFM_E_NOT_INTEGRAL / SFM_E_RANGE) instead of its own results.
+ * elem_bytes: 4 = CV_32F rows (what cv::SIFT produces), 1 = CV_8U rows. */
+SFM_API int sfm_upload_descriptors_async(sfm_ctx* ctx, int n_img, const void* const* desc,
+                                 const int32_t* n_desc, int dim, int elem_bytes);
+
 /* Binary descriptors for the reference's LIVE configuration: AKAZE descriptors (61 bytes,
  * CV_8U) matched with BFMatcher(NORM_HAMMING2) (NViewReconstuct.cpp:797, :875-877).
  * desc_u8[i] is a row-major n_desc[i] x bytes uint8 matrix, 1 <= bytes <= 64.  After this

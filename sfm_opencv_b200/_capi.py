@@ -34,6 +34,7 @@ SYMBOLS = {
     "sfm_host_free": (None, [_vp]),
     "sfm_upload_descriptors": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_upload_descriptors_u8": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
+    "sfm_upload_descriptors_async": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i, _i]),
     "sfm_upload_descriptors_bin": (_i, [_vp, _i, C.POINTER(_vp), _pi, _i]),
     "sfm_reproject_jacobians": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _pd, _pd, _i, _pf]),
     "sfm_probe_fp64_peak": (_i, [_vp, _i, C.POINTER(C.c_double)]),

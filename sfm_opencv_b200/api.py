@@ -26,6 +26,30 @@ KNN_DTYPE = np.dtype([("trainIdx0", "<i4"), ("trainIdx1", "<i4"), ("distance0", 
                       ("distance1", "<f4")])
 
 
+class PairLists:
+    """Per-pair views of one CSR result array (matches_for_all[i] of the reference): behaves
+    like a list of arrays, but a view is only created when a pair is looked at -- building
+    19,900 numpy slices eagerly costs more host time than fetching the matches."""
+
+    def __init__(self, flat: np.ndarray, offsets: np.ndarray):
+        self.flat, self.offsets = flat, offsets
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, p):
+        if isinstance(p, slice):
+            return [self[i] for i in range(*p.indices(len(self)))]
+        if p < 0:
+            p += len(self)
+        if not 0 <= p < len(self):
+            raise IndexError(p)
+        return self.flat[self.offsets[p]:self.offsets[p + 1]]
+
+    def __iter__(self):
+        return (self[p] for p in range(len(self)))
+
+
 def _ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
@@ -80,8 +104,11 @@ class Context:
         return int(self._lib.sfm_launch_count(self._h))
 
     # ------------------------------------------------------------------ matching
-    def upload_descriptors(self, descriptor_for_all, norm: str = "l2"):
+    def upload_descriptors(self, descriptor_for_all, norm: str = "l2", overlap: bool = False):
         """descriptor_for_all: list of [n_i,128] arrays, float32 (as cv::SIFT gives) or uint8.
+        overlap=True queues the transfer and returns (sfm_upload_descriptors_async): the next
+        match_pairs overlaps it with the matching kernels and raises its validation errors; the
+        arrays must stay alive (and unchanged) until then.
         norm="hamming2": list of [n_i,B<=64] uint8 binary descriptors (AKAZE: B=61), matched
         with cv::NORM_HAMMING2 as the live reference does (NViewReconstuct.cpp:797,876)."""
         descs = [np.ascontiguousarray(d) for d in descriptor_for_all]
@@ -107,8 +134,13 @@ class Context:
         dim = dims.pop() if len(dims) == 1 else -1
         n = np.array([d.shape[0] for d in descs], np.int32)
         ptrs = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs])
-        fn = self._lib.sfm_upload_descriptors_u8 if is_u8 else self._lib.sfm_upload_descriptors
-        self._check(fn(self._h, len(descs), ptrs, _ptr(n, C.c_int32), dim))
+        if overlap:
+            self._pending_upload = descs            # keep the host arrays alive
+            self._check(self._lib.sfm_upload_descriptors_async(self._h, len(descs), ptrs,
+                                                               _ptr(n, C.c_int32), dim, 1 if is_u8 else 4))
+        else:
+            fn = self._lib.sfm_upload_descriptors_u8 if is_u8 else self._lib.sfm_upload_descriptors
+            self._check(fn(self._h, len(descs), ptrs, _ptr(n, C.c_int32), dim))
         self.n_desc = [int(x) for x in n]
 
     def _pinned(self, name: str, nbytes: int) -> np.ndarray:
@@ -160,7 +192,7 @@ class Context:
         if copy:
             out = out.copy()
         self.last_d2h_bytes = total * MATCH_DTYPE.itemsize + offsets.nbytes + 4 * n_pairs
-        matches = [out[offsets[p]:offsets[p + 1]] for p in range(n_pairs)]
+        matches = PairLists(out, offsets) if n_pairs else []
         knn_list = None
         if want_knn:
             knn_list, r = [], 0

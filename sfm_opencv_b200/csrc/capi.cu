@@ -32,6 +32,8 @@ cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pa
                                 const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
                                 cudaStream_t s);
 cudaError_t launch_knn_to_float(const Knn2* knn, int64_t n, sfm_knn2_t* out, cudaStream_t s);
+cudaError_t launch_build_items(const int2* ordoff, int n_pairs, const PairDesc* pairs, int qblock,
+                               int2* items, cudaStream_t s);
 // match_hamming.cu
 cudaError_t launch_bin_pack(const uint8_t* src, int n, int bytes, int row0, uint8_t* bank,
                             cudaStream_t s);
@@ -97,6 +99,13 @@ struct sfm_ctx {
   int n_sms = 0;
   size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;
+  // asynchronous descriptor upload (sfm_upload_descriptors_async): copies + pack kernels run on
+  // their own stream, one event per image; matching kernels wait only for the images they read
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> img_ev;
+  cudaEvent_t upload_done = nullptr;
+  uint32_t* h_flags = nullptr;          // pinned: validation flags of the pending upload
+  bool upload_pending = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[2] = {nullptr, nullptr};   // sfm_timer_start / sfm_timer_stop
   std::string err;
@@ -108,8 +117,11 @@ struct sfm_ctx {
   DevBuf desc, norm, ckey, gmin8, flags, stage, img_min;   // img_min: min |row|^2 per image
   std::vector<int32_t> img_min_norm;
   std::vector<int32_t> img_n, img_row0;
-  std::vector<int2> h_items;                   // reused host staging of the work-item table
+  std::vector<int2> h_items;                   // reused host staging: (pair, first work item) per pair
+  std::vector<PairDesc> h_pairs;
+  DevBuf ordoff;
   std::vector<int32_t> h_order;                // processing order of the pairs (L2 blocking)
+  std::vector<std::pair<int64_t, int>> h_groups;   // per L2 block: first work item, last image read
   int64_t bank_rows = 0;
   bool bank_ready = false;
   bool bank_binary = false;   // false: u8 x 128 (NORM_L2); true: 128-byte expanded rows (NORM_HAMMING2)
@@ -202,6 +214,12 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     delete ctx;
     return bail(SFM_E_CUDA, "cudaStreamCreate failed");
   }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->upload_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&ctx->h_flags), 64) != cudaSuccess) {
+    sfm_destroy(ctx);
+    return bail(SFM_E_CUDA, "cannot create the copy stream");
+  }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   for (auto& ev : ctx->tev) cudaEventCreate(&ev);
   void* fn = nullptr;
@@ -221,9 +239,15 @@ sfm_ctx* sfm_create(int device_id, int* err) {
 void sfm_destroy(sfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& ev : ctx->img_ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
-                    &ctx->partial, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -288,12 +312,40 @@ static int make_tmap(sfm_ctx* ctx, CUtensorMap* tm, void* base, uint64_t rows, u
   return SFM_OK;
 }
 
+// Outcome of the validation flags the pack kernels accumulate.
+static int check_upload_flags(sfm_ctx* ctx, uint32_t flags) {
+  if (flags & 2u) return fail(ctx, SFM_E_RANGE, "descriptor value outside 0..255");
+  if (flags & 1u) return fail(ctx, SFM_E_NOT_INTEGRAL, "descriptor holds a non-integer value");
+  if (flags & 4u)
+    return fail(ctx, SFM_E_RANGE,
+                "descriptor row norm^2 >= 2^21: float sqrt no longer injective on the distances");
+  return SFM_OK;
+}
+
+// Waits for a pending asynchronous upload and reports its validation result.
+static int finish_upload(sfm_ctx* ctx) {
+  if (!ctx->upload_pending) return SFM_OK;
+  CK(cudaEventSynchronize(ctx->upload_done));
+  ctx->upload_pending = false;
+  const int rc = check_upload_flags(ctx, *ctx->h_flags);
+  if (rc) {                               // the kernels queued on bad data finish, results are dropped
+    ctx->bank_ready = false;
+    cudaStreamSynchronize(ctx->stream);
+  }
+  return rc;
+}
+
 static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const int32_t* n_desc,
-                         int dim, bool f32) {
+                         int dim, bool f32, bool async) {
   if (!ctx) return SFM_E_INVALID;
   if (n_img <= 0 || !desc || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
   if (dim != kDim) return fail(ctx, SFM_E_DIM, "descriptor dimension must be 128 (SIFT)");
   CK(cudaSetDevice(ctx->device));
+  if (ctx->upload_pending) {            // a previous asynchronous upload still owns the staging area
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->upload_pending = false;
+  }
+  cudaStream_t up = async ? ctx->copy_stream : ctx->stream;
   ctx->bank_ready = false;
   ctx->last_valid = false;
   ctx->img_n.assign(n_desc, n_desc + n_img);
@@ -317,35 +369,48 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   CK(ctx->gmin8.ensure(static_cast<size_t>(rows) / 8 * 4 + 64));
   CK(ctx->flags.ensure(4));
   CK(ctx->img_min.ensure(4 * static_cast<size_t>(n_img)));
-  CK(cudaMemsetAsync(ctx->img_min.p, 0x7f, 4 * static_cast<size_t>(n_img), ctx->stream));
+  if (async) {
+    while (ctx->img_ev.size() < static_cast<size_t>(n_img)) {
+      cudaEvent_t e = nullptr;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->img_ev.push_back(e);
+    }
+  }
+  CK(cudaMemsetAsync(ctx->img_min.p, 0x7f, 4 * static_cast<size_t>(n_img), up));
   const size_t elt = f32 ? 4 : 1;
   const size_t img_bytes = static_cast<size_t>(max_n) * kDim * elt;
   CK(ctx->stage.ensure(2 * img_bytes + 512));
-  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, ctx->stream));
-  CK(cudaMemsetAsync(ctx->flags.p, 0, 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, up));
+  CK(cudaMemsetAsync(ctx->flags.p, 0, 4, up));
   for (int i = 0; i < n_img; ++i) {
     // alternate staging halves; copies and pack kernels are ordered by the single stream
     uint8_t* st = ctx->stage.as<uint8_t>() + (i & 1) * ((img_bytes + 255) / 256 * 256);
     const size_t bytes = static_cast<size_t>(n_desc[i]) * kDim * elt;
-    if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, up));
     CK(launch_pack_rows(f32, st, n_desc[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
                         ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
-                        ctx->flags.as<uint32_t>(), ctx->img_min.as<int32_t>() + i, ctx->stream));
+                        ctx->flags.as<uint32_t>(), ctx->img_min.as<int32_t>() + i, up));
     ctx->launches += 3;
+    if (async) CK(cudaEventRecord(ctx->img_ev[i], up));      // image i is resident after this
   }
-  uint32_t flags = 0;
   ctx->img_min_norm.assign(n_img, 0);
-  CK(cudaMemcpyAsync(ctx->img_min_norm.data(), ctx->img_min.p, 4 * static_cast<size_t>(n_img),
-                     cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (flags & 2u) return fail(ctx, SFM_E_RANGE, "descriptor value outside 0..255");
-  if (flags & 1u) return fail(ctx, SFM_E_NOT_INTEGRAL, "descriptor holds a non-integer value");
-  if (flags & 4u)
-    return fail(ctx, SFM_E_RANGE,
-                "descriptor row norm^2 >= 2^21: float sqrt no longer injective on the distances");
   int rc = make_tmap(ctx, &ctx->tmap, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
   if (rc) return rc;
+  if (async) {
+    // return at once: sfm_match_pairs makes its kernels wait for the images they read and
+    // reports the validation result of this upload
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
+    CK(cudaEventRecord(ctx->upload_done, up));
+    ctx->upload_pending = true;
+  } else {
+    uint32_t flags = 0;
+    CK(cudaMemcpyAsync(ctx->img_min_norm.data(), ctx->img_min.p, 4 * static_cast<size_t>(n_img),
+                       cudaMemcpyDeviceToHost, up));
+    CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
+    CK(cudaStreamSynchronize(up));
+    rc = check_upload_flags(ctx, flags);
+    if (rc) return rc;
+  }
   ctx->bank_binary = false;
   ctx->bank_ready = true;
   return SFM_OK;
@@ -354,13 +419,20 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
 int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* desc_f32,
                            const int32_t* n_desc, int dim) {
   return upload_common(ctx, n_img, reinterpret_cast<const void* const*>(desc_f32), n_desc, dim,
-                       true);
+                       true, false);
 }
 
 int sfm_upload_descriptors_u8(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
                               const int32_t* n_desc, int dim) {
   return upload_common(ctx, n_img, reinterpret_cast<const void* const*>(desc_u8), n_desc, dim,
-                       false);
+                       false, false);
+}
+
+int sfm_upload_descriptors_async(sfm_ctx* ctx, int n_img, const void* const* desc,
+                                 const int32_t* n_desc, int dim, int elem_bytes) {
+  if (elem_bytes != 4 && elem_bytes != 1)
+    return fail(ctx, SFM_E_INVALID, "elem_bytes must be 4 (CV_32F) or 1 (CV_8U)");
+  return upload_common(ctx, n_img, desc, n_desc, dim, elem_bytes == 4, true);
 }
 
 // Binary descriptors for NORM_HAMMING2 (the live AKAZE path, NViewReconstuct.cpp:797,876).
@@ -372,6 +444,10 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
   if (bytes <= 0 || bytes > kBinMaxBytes)
     return fail(ctx, SFM_E_DIM, "binary descriptors must be 1..64 bytes (AKAZE: 61)");
   CK(cudaSetDevice(ctx->device));
+  if (ctx->upload_pending) {
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->upload_pending = false;
+  }
   ctx->bank_ready = false;
   ctx->last_valid = false;
   ctx->img_n.assign(n_desc, n_desc + n_img);
@@ -420,9 +496,11 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     return fail(ctx, SFM_E_INVALID, "null pair list");
   CK(cudaSetDevice(ctx->device));
   const int n_img = static_cast<int>(ctx->img_n.size());
-  std::vector<PairDesc> pairs(n_pairs);
-  std::vector<int2>& items = ctx->h_items;    // work items: (pair, 256-row query block)
-  items.clear();
+  std::vector<PairDesc>& pairs = ctx->h_pairs;
+  pairs.resize(n_pairs);
+  std::vector<int2>& ordoff = ctx->h_items;   // per pair in processing order: (pair, first work item)
+  ordoff.clear();
+  int64_t n_items = 0;                        // work items: (pair, 256-row query block)
   int64_t rows = 0;
   int32_t max_n = 1;
   for (int p = 0; p < n_pairs; ++p) {
@@ -455,20 +533,28 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     for (int p = 0; p < n_pairs; ++p) order[p] = p;
     std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
       const int qa = pair_q[a] / B, qb = pair_q[b] / B, ta = pair_t[a] / B, tb = pair_t[b] / B;
-      if (qa != qb) return qa < qb;
-      if (ta != tb) return ta < tb;
+      if (ta != tb) return ta < tb;      // train block outermost: an asynchronous upload is
+      if (qa != qb) return qa < qb;      // consumed in image order (block (qb, tb) needs images < (tb+1) B)
       if (pair_q[a] != pair_q[b]) return pair_q[a] < pair_q[b];
       if (pair_t[a] != pair_t[b]) return pair_t[a] < pair_t[b];
       return a < b;
     });
     const int qblock = ctx->bank_binary ? 128 : kTileM;   // query rows per work item
+    ctx->h_groups.clear();                                // (first item, last image needed) per block
+    int cur_q = -1, cur_t = -1;
     for (int32_t p : order) {
-      const int mb = (pairs[p].nq + qblock - 1) / qblock;
-      for (int m = 0; m < mb; ++m) items.push_back(make_int2(p, m));
-      if (items.size() > static_cast<size_t>(INT32_MAX)) return fail(ctx, SFM_E_INVALID, "too many query blocks");
+      const int qb = pair_q[p] / B, tb = pair_t[p] / B;
+      if (qb != cur_q || tb != cur_t) {
+        ctx->h_groups.push_back(std::make_pair(n_items, 0));
+        cur_q = qb;
+        cur_t = tb;
+      }
+      ctx->h_groups.back().second = std::max(ctx->h_groups.back().second, std::max(pair_q[p], pair_t[p]));
+      ordoff.push_back(make_int2(p, static_cast<int>(n_items)));
+      n_items += (pairs[p].nq + qblock - 1) / qblock;
+      if (n_items > INT32_MAX) return fail(ctx, SFM_E_INVALID, "too many query blocks");
     }
   }
-  const int64_t n_items = static_cast<int64_t>(items.size());
   *total_rows = rows;
   CK(ctx->pairs.ensure(sizeof(PairDesc) * (n_pairs + 1)));
   CK(ctx->items.ensure(sizeof(int2) * (n_items + 1)));
@@ -479,9 +565,15 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   if (n_pairs)
     CK(cudaMemcpyAsync(ctx->pairs.p, pairs.data(), sizeof(PairDesc) * n_pairs,
                        cudaMemcpyHostToDevice, ctx->stream));
-  if (n_items)
-    CK(cudaMemcpyAsync(ctx->items.p, items.data(), sizeof(int2) * n_items, cudaMemcpyHostToDevice,
+  if (n_pairs) {
+    // the (pair, block) table is expanded on the device from 8 bytes per pair
+    CK(ctx->ordoff.ensure(sizeof(int2) * (n_pairs + 1)));
+    CK(cudaMemcpyAsync(ctx->ordoff.p, ordoff.data(), sizeof(int2) * n_pairs, cudaMemcpyHostToDevice,
                        ctx->stream));
+    CK(launch_build_items(ctx->ordoff.as<int2>(), n_pairs, ctx->pairs.as<PairDesc>(),
+                          ctx->bank_binary ? 128 : kTileM, ctx->items.as<int2>(), ctx->stream));
+    ctx->launches += 1;
+  }
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (ctx->bank_binary) {
     // NORM_HAMMING2: split every train image over enough blocks to fill the device
@@ -496,17 +588,32 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
                            ctx->knn.as<Knn2>(), ctx->stream));
     if (n_items > 0) ctx->launches += 2;
   } else {
-    CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
-                   ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
-                   static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
-    if (n_items > 0) ctx->launches += 1;
+    if (ctx->upload_pending) {
+      // one launch per L2 block, each waiting only for the last image it reads: matching
+      // starts while later images are still crossing PCIe
+      for (size_t g = 0; g < ctx->h_groups.size(); ++g) {
+        const int64_t first = ctx->h_groups[g].first;
+        const int64_t last = g + 1 < ctx->h_groups.size() ? ctx->h_groups[g + 1].first : n_items;
+        if (last <= first) continue;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->img_ev[ctx->h_groups[g].second], 0));
+        CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
+                       ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>() + first,
+                       static_cast<int>(last - first), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+        ctx->launches += 1;
+      }
+    } else {
+      CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
+                     ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
+                     static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+      if (n_items > 0) ctx->launches += 1;
+    }
   }
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
                    gate_mult, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
                    ctx->offsets.as<int64_t>(), ctx->stream));
   ctx->launches += (n_pairs > 0 ? 2 : 1);
-  return SFM_OK;
+  return finish_upload(ctx);     // no-op unless an asynchronous upload is pending: its verdict
 }
 
 // Writes the kept matches of the last sfm_match_pairs* call (still resident) to the host.

@@ -232,12 +232,34 @@ __global__ void knn_to_float_kernel(const Knn2* __restrict__ knn, int64_t n,
   *reinterpret_cast<int4*>(&out[i]) = o;
 }
 
+// Work-item table of the kNN kernels: pair p (visited in the host's processing order) owns the
+// items [first, first + ceil(nq / qblock)), item k = (p, k - first).  One warp per pair.
+__global__ void build_items_kernel(const int2* __restrict__ ordoff, int n_pairs,
+                                   const PairDesc* __restrict__ pairs, int qblock,
+                                   int2* __restrict__ items) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_pairs) return;
+  const int2 po = ordoff[w];
+  const int mb = (pairs[po.x].nq + qblock - 1) / qblock;
+  for (int m = lane; m < mb; m += 32) items[po.y + m] = make_int2(po.x, m);
+}
+
 // ------------------------------------------------------------------------------- launchers
+cudaError_t launch_build_items(const int2* ordoff, int n_pairs, const PairDesc* pairs, int qblock,
+                               int2* items, cudaStream_t s) {
+  if (n_pairs > 0)
+    build_items_kernel<<<(n_pairs * 32 + 127) / 128, 128, 0, s>>>(ordoff, n_pairs, pairs, qblock, items);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
                              int32_t* norm, int32_t* ckey, int32_t* gmin8, uint32_t* flags,
                              int32_t* min_norm, cudaStream_t s) {
+  // 128-thread CTAs (<= 24 registers per thread): they fit next to a resident kNN CTA (768 threads,
+  // 61440 of the SM's 65536 registers), so an asynchronous upload keeps packing while the
+  // matching kernel owns every SM
   if (n > 0) {
-    const int warps = 8;
+    const int warps = 4;
     const int grid = (n + warps - 1) / warps;
     if (f32)
       pack_rows_kernel<true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags,
@@ -247,8 +269,8 @@ cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t
                                                           min_norm);
   }
   const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
-  if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 255) / 256, 256, 0, s>>>(n, n_pad, row0, norm, ckey);
-  if (n_pad > 0) group_min_kernel<<<(n_pad / 8 + 255) / 256, 256, 0, s>>>(norm, row0, n_pad, gmin8);
+  if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 127) / 128, 128, 0, s>>>(n, n_pad, row0, norm, ckey);
+  if (n_pad > 0) group_min_kernel<<<(n_pad / 8 + 127) / 128, 128, 0, s>>>(norm, row0, n_pad, gmin8);
   return cudaGetLastError();
 }
 

@@ -335,3 +335,46 @@ def test_matches_only_equals_knn_call_all_pairs(ctx):
     assert np.array_equal(mda.view(np.uint32), mdb.view(np.uint32))
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_async_upload_overlapped_with_matching(ctx):
+    """sfm_upload_descriptors_async: kernels wait per image; results equal the synchronous path."""
+    sizes = [900, 300, 1300, 64, 513, 2300, 700]
+    bank = [synth.sift_like(n, 240 + i) for i, n in enumerate(sizes)]
+    for j in range(1, len(bank)):
+        k = min(len(bank[j]), len(bank[j - 1])) // 4
+        bank[j][:k] = bank[j - 1][k:2 * k]
+    pairs = M.all_pairs(len(bank)) + [(5, 0), (2, 2)]
+    ctx.upload_descriptors(bank)
+    want, wmd, wknn = ctx.match_pairs(pairs, want_knn=True)
+    for as_float in (True, False):
+        host = [b.astype(np.float32) if as_float else b for b in bank]
+        for _ in range(2):                                   # twice: the staging area is reused
+            ctx.upload_descriptors(host, overlap=True)
+            got, gmd, gknn = ctx.match_pairs(pairs, want_knn=True)
+            assert np.array_equal(gmd.view(np.uint32), wmd.view(np.uint32))
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b)
+            for a, b in zip(gknn, wknn):
+                assert np.array_equal(a, b)
+    tot, _, _ = ctx.match_pairs_resident(pairs)              # resident path after a sync upload
+    assert tot == sum(len(x) for x in want)
+
+
+def test_async_upload_reports_validation_errors_at_match(ctx):
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    bank = [synth.sift_like(300, 1).astype(np.float32), synth.sift_like(300, 2).astype(np.float32)]
+    bank[1][17, 5] = 3.5
+    ctx.upload_descriptors(bank, overlap=True)               # queued: no error yet
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.match_pairs([(0, 1)])
+    assert e.value.code == _capi.SFM_E_NOT_INTEGRAL
+    with pytest.raises(sfm.SfmError) as e:                   # the bank is not usable afterwards
+        ctx.match_pairs([(0, 1)])
+    assert e.value.code == _capi.SFM_E_NOT_UPLOADED
+    good = synth.image_bank(2, 300, seed0=1)
+    ctx.upload_descriptors(good, overlap=True)
+    m, _, _ = ctx.match_pairs([(0, 1)])
+    om, _, _, _, _ = M.match_features(good[0], good[1])
+    assert np.array_equal(m[0]["trainIdx"], om[:, 1])
