@@ -433,6 +433,15 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     int neg2 = -2;
     asm volatile("" : "+r"(t_addr), "+r"(bar_tf), "+r"(bar_te), "+r"(ck_base), "+r"(gm_base),
                  "+r"(neg2));
+#ifndef SFM_EXP_NOUNIFORM
+    // warp-uniform by construction (functions of the warp index): a broadcast lets ptxas see
+    // it and keep the address arithmetic of the tile loop on the uniform datapath
+    t_addr = __shfl_sync(0xffffffffu, t_addr, 0);
+    bar_tf = __shfl_sync(0xffffffffu, bar_tf, 0);
+    bar_te = __shfl_sync(0xffffffffu, bar_te, 0);
+    ck_base = __shfl_sync(0xffffffffu, ck_base, 0);
+    gm_base = __shfl_sync(0xffffffffu, gm_base, 0);
+#endif
     const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
     const uint32_t share_own = smem_base + kOffShare + row_in_blk * 32 + chalf * 16;
     const uint32_t share_other = smem_base + kOffShare + row_in_blk * 32 + (chalf ^ 1) * 16;
@@ -449,6 +458,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         mbar_wait(bar_tf + 16 * buf, bphase);
         tc_fence_after();
         ntiles = info[abuf].ntiles;
+#ifndef SFM_EXP_NOUNIFORM
+        ntiles = __shfl_sync(0xffffffffu, ntiles, 0);
+#endif
         rows_valid = info[abuf].rows_valid;
         norm_row = info[abuf].norm_row;
         knn_row = info[abuf].knn_row;
@@ -467,7 +479,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_te + 16 * buf);        // tile t is out of TMEM
+          mbar_arrive_elected(bar_te + 16 * buf);               // tile t is out of TMEM
           const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
           if (t + 1 < ntiles) {
             mbar_wait(bar_tf + 16 * nbuf, nphase);

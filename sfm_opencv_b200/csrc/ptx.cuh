@@ -39,6 +39,16 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival from whichever lane elect.sync picks (all lanes of the warp must call it): no
+// lane-id arithmetic, the predicate comes straight from ELECT.
+__device__ __forceinline__ void mbar_arrive_elected(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
