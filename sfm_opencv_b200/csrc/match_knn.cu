@@ -470,7 +470,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         uint32_t ra[32], rb[32];
         tmem_ld_x32(t_addr + buf * (2 * kTileN), ra);
         tmem_ld_wait();
-        for (int t = 0; t < ntiles; ++t) {
+        // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
+        // behind the inner loop, not behind a per-tile test
+        for (int w0 = 0; w0 < ntiles; w0 += kWinTiles) {
+        const int wend = min(w0 + kWinTiles, ntiles);
+        for (int t = w0; t < wend; ++t) {
           tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);    // chunk 1 in flight
           const uint32_t slot = tile_seq % kCkSlots;
           const uint32_t ck_addr = ck_base + slot * kCkBytes;
@@ -488,10 +492,14 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           }
           chunk_update<kMode>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
           if (t + 1 < ntiles) tmem_ld_wait();
-          if ((t & (kWinTiles - 1)) == kWinTiles - 1 || t == ntiles - 1) {
+          ++tile_seq;
+          buf = nbuf;
+          bphase = nphase;
+        }
+          {
             // close the 1024-column window, then tighten the bound, also with the row
             // partner's top-2 (ties with the partner's columns go by index: + 1)
-            close_window(st, (t & ~(kWinTiles - 1)) * kTileN);
+            close_window(st, w0 * kTileN);
             int bound = st.g2v;
             if (kMode == 1) {
               // the row's second best over BOTH column halves bounds what can still enter:
@@ -505,9 +513,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             }
             st.bv = bound;
           }
-          ++tile_seq;
-          buf = nbuf;
-          bphase = nphase;
         }
       } else {
         // ---- timing experiments only (results are garbage):
