@@ -162,15 +162,10 @@ __device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
 
 // exact keys of the 8 columns of a group (column keys from the shared-memory ring) -> (m1, m2)
 __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr, RowTop2& s) {
-#ifdef SFM_EXP_NOLDS   // timing experiment (results invalid): column keys without the LDS latency
-  const int4 c0 = make_int4(ck_addr, ck_addr + 1, ck_addr + 2, ck_addr + 3);
-  const int4 c1 = make_int4(ck_addr + 4, ck_addr + 5, ck_addr + 6, ck_addr + 7);
-#else
 #ifdef SFM_EXP_XLAT    // timing experiment: one more dependent shared-memory round trip per hit
   ck_addr += static_cast<uint32_t>(lds_32(ck_addr)) & 0u;
 #endif
   const int4 c0 = lds_v4(ck_addr), c1 = lds_v4(ck_addr + 16);
-#endif
   int k[8];
   k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
   k[2] = make_key(a[2], c0.z); k[3] = make_key(a[3], c0.w);
@@ -223,9 +218,7 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
     for (int j = 0; j < 4; ++j) {
       if (h[j]) {
         group_insert(&r[8 * j], ck_addr + 32 * j, s);
-#ifndef SFM_EXP_NOBV
         s.bv = min(s.bv, s.m2 >> kColBits);
-#endif
 #ifdef SFM_EXP_XALU    // timing experiment: 8 more dependent ALU ops per hit (no effect on values)
         {
           int x = s.bv;
