@@ -28,12 +28,15 @@
 // (precomputed at upload).  Per group of 8 columns: a 3-input-max tree (0.5 op/element),
 // one IMAD and one warp vote against the rows' bound.  Only groups in
 // which some row of the warp passes get their exact packed keys built (8 IMADs with the
-// column keys staged in shared memory) and inserted (20 min/max); that is harmless for the
-// rows that did not pass.  Skipped columns provably have two predecessors that beat them,
-// so results are identical to the unfiltered epilogue (SFM_KNN_MODE=0); a GPU test compares
-// the two bit for bit.  The two threads that share a row (column halves) exchange their
-// second-best value through shared memory once per 1024-column window to tighten the bound.
-// The distance matrix never leaves the SM.
+// column keys staged in shared memory) and inserted (knock-out min trees, 13 ALU ops); that is
+// harmless for the rows that did not pass.  Skipped columns provably have two predecessors
+// that beat them, so results are identical to the unfiltered epilogue (SFM_KNN_MODE=0); a GPU
+// test compares the two bit for bit.  The two threads that share a row (column halves)
+// exchange their top-2 through shared memory once per 1024-column window and bound with the
+// row's JOINT second best.  The epilogue is ALU-throughput bound: per thread
+// and 64-accumulator tile it issues 32 max + 8 compare + 8 vote instructions and 15 more per
+// group that hits; everything warp-uniform (addresses, barriers, loop control) runs on the
+// uniform datapath.  The distance matrix never leaves the SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
