@@ -58,6 +58,18 @@ def shard_range(n: int, world_size: int):
     return out
 
 
+def shard_query_rows(n_query: int, world_size: int, block: int = 256):
+    """One huge pair (BASELINE config 4): query rows are independent, so each rank matches a
+    contiguous range of query rows against the whole (replicated) train set -- no collective, the
+    k-NN rows / match lists concatenate in rank order.  Ranges are multiples of the kernel's
+    256-row query block (except the last) so that no rank pads a block another rank also holds."""
+    blocks = (int(n_query) + block - 1) // block
+    out = []
+    for s, e in shard_range(blocks, world_size):
+        out.append((min(s * block, n_query), min(e * block, n_query)))
+    return out
+
+
 def gather_match_lists(local_matches, start: int, stop: int, n_pairs: int, group=None):
     """Final host gather (the only exchange on the path): every rank contributes the match
     arrays of its pair range; rank order == pair order, so the result is the reference's

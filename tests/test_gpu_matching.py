@@ -378,3 +378,20 @@ def test_async_upload_reports_validation_errors_at_match(ctx):
     m, _, _ = ctx.match_pairs([(0, 1)])
     om, _, _, _, _ = M.match_features(good[0], good[1])
     assert np.array_equal(m[0]["trainIdx"], om[:, 1])
+
+
+def test_one_pair_sharded_by_query_rows(ctx):
+    """BASELINE config 4 across GPUs: each rank takes a query-row range of the one pair, the
+    train set is replicated, the kNN rows concatenate (emulated here with one context)."""
+    from sfm_opencv_b200.sharding import shard_query_rows
+    q = synth.sift_like(3000, 501)
+    t = synth.sift_like(5000, 502)
+    t[:700] = q[1000:1700]
+    ctx.upload_descriptors([q, t])
+    _, _, whole = ctx.match_pairs([(0, 1)], want_knn=True)
+    parts = []
+    for lo, hi in shard_query_rows(len(q), 3):
+        ctx.upload_descriptors([q[lo:hi], t])
+        _, _, k = ctx.match_pairs([(0, 1)], want_knn=True)
+        parts.append(k[0])
+    assert np.array_equal(np.concatenate(parts), whole[0])

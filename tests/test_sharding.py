@@ -35,6 +35,15 @@ def test_shard_pairs_balances_uneven_cost():
     assert S.shard_pairs(pairs[:1], n_desc, 4)[-1][1] == 1
 
 
+def test_shard_query_rows_covers_in_blocks():
+    from sfm_opencv_b200.sharding import shard_query_rows
+    for n, w in ((65536, 8), (1000, 3), (255, 4), (0, 2), (257, 2)):
+        r = shard_query_rows(n, w)
+        assert len(r) == w and r[0][0] == 0 and r[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(s % 256 == 0 for s, _ in r if s < n)
+
+
 def test_shard_range():
     assert S.shard_range(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert S.shard_range(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
