@@ -209,6 +209,14 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
     for (int j = 0; j < 4; ++j)
       h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
 #endif
+#ifdef SFM_EXP_XVOTE   // timing experiment: 4 more votes per chunk (vote.all next to vote.any)
+    {
+      bool v = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v |= __all_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+      if (v) s.g1i ^= 1;     // all 32 rows pass at once: practically never after the first tiles
+    }
+#endif
 #ifdef SFM_EXP_XFAST   // timing experiment: 4 more independent ALU ops per chunk in the fast path
     {
       int x0 = s.g1i, x1 = s.g2i, x2 = s.g1i, x3 = s.g2i;
