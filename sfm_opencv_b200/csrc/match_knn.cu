@@ -42,6 +42,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "match_types.h"
 #include "ptx.cuh"
 
@@ -63,6 +65,7 @@ constexpr int kRegsEpi = 104;                   // setmaxnreg: epilogue warpgrou
 static_assert(4 * kRegsProd + 4 * kRegsMma + 16 * kRegsEpi <= 24 * 80,
               "register pool of the CTA (768 x 80)");
 constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-key window (8)
+constexpr int kPreVoteTiles = 128;              // sweeps of >= 16384 train rows use the chunk pre-vote
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
 constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
@@ -191,7 +194,12 @@ __device__ __forceinline__ int group_max(const uint32_t* r) {
 //            warp: per group one IMAD, one compare and one vote on top of the max tree.
 //            neg2 = -2 in a register ptxas cannot see through, so that the multiply-add stays
 //            an IMAD on the FMA pipe instead of an IADD3 on the (limiting) ALU pipe.
-template <int kMode>
+//   kPreVote : one vote for the whole chunk in front of the four per-group votes.  A vote costs
+//            about two ALU instructions; in long sweeps (rare hits) most chunks need only that
+//            one, in 8192-column sweeps 54 % of the chunks contain a hit and it does not pay
+//            (measured: -2.6 % there, +7 % on a 65536-column train image), so the kernel picks
+//            per work item.
+template <int kMode, bool kPreVote>
 __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
                                              uint32_t gm_addr, int neg2, RowTop2& s) {
   if constexpr (kMode == 0) {
@@ -205,9 +213,18 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
 #pragma unroll
     for (int j = 0; j < 4; ++j) h[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
 #else
+    if constexpr (kPreVote) {
+      bool p[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+      for (int j = 0; j < 4; ++j) p[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
+      if (!__any_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3])) return;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __any_sync(0xffffffffu, p[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
+    }
 #endif
 #ifdef SFM_EXP_XVOTE   // timing experiment: 4 more votes per chunk (vote.all next to vote.any)
     {
@@ -474,6 +491,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         uint32_t ra[32], rb[32];
         tmem_ld_x32(t_addr + buf * (2 * kTileN), ra);
         tmem_ld_wait();
+        // the sweep in two compiled flavours (with / without the chunk-level pre-vote, see
+        // chunk_update); long train images take the pre-vote one
+        auto sweep = [&](auto pre_tag) {
+          constexpr bool kPre = decltype(pre_tag)::value;
         // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
         // behind the inner loop, not behind a per-tile test
         for (int w0 = 0; w0 < ntiles; w0 += kWinTiles) {
@@ -483,7 +504,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           const uint32_t slot = tile_seq % kCkSlots;
           const uint32_t ck_addr = ck_base + slot * kCkBytes;
           const uint32_t gm_addr = gm_base + slot * kGmBytes;
-          chunk_update<kMode>(ra, ck_addr, gm_addr, neg2, st);
+          chunk_update<kMode, kPre>(ra, ck_addr, gm_addr, neg2, st);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -494,7 +515,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             tc_fence_after();
             tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1 in flight
           }
-          chunk_update<kMode>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+          chunk_update<kMode, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
           if (t + 1 < ntiles) tmem_ld_wait();
           ++tile_seq;
           buf = nbuf;
@@ -518,6 +539,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             st.bv = bound;
           }
         }
+        };
+        if (ntiles >= kPreVoteTiles) sweep(std::true_type{});
+        else sweep(std::false_type{});
       } else {
         // ---- timing experiments only (results are garbage):
         // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
