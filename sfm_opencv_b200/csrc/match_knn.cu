@@ -65,6 +65,9 @@ constexpr int kRegsEpi = 104;                   // setmaxnreg: epilogue warpgrou
 static_assert(4 * kRegsProd + 4 * kRegsMma + 16 * kRegsEpi <= 24 * 80,
               "register pool of the CTA (768 x 80)");
 constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-key window (8)
+#ifndef SFM_COLD_WINDOWS
+#define SFM_COLD_WINDOWS 1                      // windows at the start of a sweep that skip the filter
+#endif
 constexpr int kPreVoteTiles = 128;              // sweeps of >= 16384 train rows use the chunk pre-vote
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
@@ -493,18 +496,19 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         tmem_ld_wait();
         // the sweep in two compiled flavours (with / without the chunk-level pre-vote, see
         // chunk_update); long train images take the pre-vote one
-        auto sweep = [&](auto pre_tag) {
+        auto sweep = [&](auto mode_tag, auto pre_tag, int w_first, int w_last) {
+          constexpr int kM = decltype(mode_tag)::value;      // 0: insert every group, 1: filtered
           constexpr bool kPre = decltype(pre_tag)::value;
         // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
         // behind the inner loop, not behind a per-tile test
-        for (int w0 = 0; w0 < ntiles; w0 += kWinTiles) {
+        for (int w0 = w_first; w0 < w_last; w0 += kWinTiles) {
         const int wend = min(w0 + kWinTiles, ntiles);
         for (int t = w0; t < wend; ++t) {
           tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);    // chunk 1 in flight
           const uint32_t slot = tile_seq % kCkSlots;
           const uint32_t ck_addr = ck_base + slot * kCkBytes;
           const uint32_t gm_addr = gm_base + slot * kGmBytes;
-          chunk_update<kMode, kPre>(ra, ck_addr, gm_addr, neg2, st);
+          chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -515,7 +519,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             tc_fence_after();
             tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1 in flight
           }
-          chunk_update<kMode, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+          chunk_update<kM, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
           if (t + 1 < ntiles) tmem_ld_wait();
           ++tile_seq;
           buf = nbuf;
@@ -540,8 +544,14 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           }
         }
         };
-        if (ntiles >= kPreVoteTiles) sweep(std::true_type{});
-        else sweep(std::false_type{});
+        // The first windows of a sweep run unfiltered: while the top-2 of a row is still cold
+        // 65-100 % of the groups hit for some row of the warp, and testing them first (max tree,
+        // compare, vote, branch) costs more than it saves.
+        constexpr int kCold = kMode == 1 ? SFM_COLD_WINDOWS * kWinTiles : 0;
+        const int cold = min(kCold, ntiles);
+        if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, 0, cold);
+        if (ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, cold, ntiles);
+        else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, cold, ntiles);
       } else {
         // ---- timing experiments only (results are garbage):
         // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
