@@ -202,12 +202,17 @@ __device__ __forceinline__ int group_max(const uint32_t* r) {
 //            one, in 8192-column sweeps 54 % of the chunks contain a hit and it does not pay
 //            (measured: -2.6 % there, +7 % on a 65536-column train image), so the kernel picks
 //            per work item.
-template <int kMode, bool kPreVote>
+// `mid` runs once inside the update, after the filter votes and before the inserts (the sweep
+// hands the TMEM buffer back there).
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <int kMode, bool kPreVote, class Mid = NoHook>
 __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
-                                             uint32_t gm_addr, int neg2, RowTop2& s) {
+                                             uint32_t gm_addr, int neg2, RowTop2& s, Mid mid = Mid()) {
   if constexpr (kMode == 0) {
+    group_insert(&r[0], ck_addr, s);
+    mid();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
+    for (int j = 1; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
   } else {
     const int4 nn = lds_v4(gm_addr);
     const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
@@ -220,7 +225,7 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
       bool p[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) p[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
-      if (!__any_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3])) return;
+      if (!__any_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3])) { mid(); return; }
 #pragma unroll
       for (int j = 0; j < 4; ++j) h[j] = __any_sync(0xffffffffu, p[j]);
     } else {
@@ -245,6 +250,7 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
       if ((x0 ^ x1 ^ x2 ^ x3) == 0x12345677) s.g1i = x0;
     }
 #endif
+    mid();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (h[j]) {
@@ -476,9 +482,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       int ntiles = 1, rows_valid = 0, norm_row = 0;
       int64_t knn_row = 0;
       if constexpr (kMode <= 1) {
-        // ---- software-pipelined sweep: a tile is two 32-column chunks per thread; the
-        // tcgen05.ld of the next chunk is in flight while the current one is processed, so
-        // the TMEM read latency is off the warp's per-tile instruction chain
+        // ---- sweep: a tile is two 32-column chunks per thread; the tcgen05.ld of chunk 1 is
+        // in flight while chunk 0 is processed, and the buffer is released between the two
         mbar_wait(bar_tf + 16 * buf, bphase);
         tc_fence_after();
         ntiles = info[abuf].ntiles;
@@ -508,19 +513,32 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           const uint32_t slot = tile_seq % kCkSlots;
           const uint32_t ck_addr = ck_base + slot * kCkBytes;
           const uint32_t gm_addr = gm_base + slot * kGmBytes;
-          chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          mbar_arrive_elected(bar_te + 16 * buf);               // tile t is out of TMEM
+          auto release = [&] {                                  // tile t is out of TMEM
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            mbar_arrive_elected(bar_te + 16 * buf);
+          };
+          if constexpr (kPre) {
+            chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st);
+            release();
+          } else {
+            // released from inside chunk 0 (after its votes, before its inserts): chunk 1 has
+            // landed by then, and the MMA of tile t+2 starts a third of a tile earlier (+0.9 %)
+            chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st, release);
+          }
           const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
+          chunk_update<kM, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+          // Tile t+1 is asked for only now, not before chunk 1: the 8 warps that share a TMEM
+          // buffer drift apart by their hit counts, and the MMA of tile t+1 starts when the
+          // slowest of them released tile t-1 -- waiting half a tile later keeps 44 % of the
+          // waits from sleeping (measured: +5 %, more than the exposed tcgen05.ld costs)
           if (t + 1 < ntiles) {
             mbar_wait(bar_tf + 16 * nbuf, nphase);
             tc_fence_after();
-            tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1 in flight
+            tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1
+            tmem_ld_wait();
           }
-          chunk_update<kM, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
-          if (t + 1 < ntiles) tmem_ld_wait();
           ++tile_seq;
           buf = nbuf;
           bphase = nphase;
