@@ -22,7 +22,12 @@ int main(int argc, char** argv) {
                        (const void*)sfm_write_ply_binary, (const void*)sfm_triangulate_batch_timed,
                        (const void*)sfm_reproject_residuals_timed, (const void*)sfm_probe_i8_peak,
                        (const void*)sfm_probe_fp64_peak, (const void*)sfm_launch_count,
-                       (const void*)sfm_timer_start, (const void*)sfm_timer_stop, (const void*)sfm_sync};
+                       (const void*)sfm_timer_start, (const void*)sfm_timer_stop, (const void*)sfm_sync,
+                       (const void*)sfm_bank_layout, (const void*)sfm_bank_upload_range,
+                       (const void*)sfm_bank_commit, (const void*)sfm_bank_image_rows,
+                       (const void*)sfm_bank_rows_dev, (const void*)sfm_bank_copy_peer,
+                       (const void*)sfm_match_rows_begin, (const void*)sfm_match_rows_finish,
+                       (const void*)sfm_ba_create, (const void*)sfm_ba_evaluate, (const void*)sfm_ba_destroy};
   size_t n = sizeof fns / sizeof fns[0], i;
   for (i = 0; i < n; ++i)
     if (!fns[i]) return 2;

@@ -23,7 +23,9 @@
  *     entry point fails with SFM_E_NO_DEVICE / SFM_E_CUDA.
  *   - a context is bound to ONE device and is not thread-safe; use one
  *     context per host thread / per GPU (pairs, points and observations are
- *     independent, so callers shard them over contexts).
+ *     independent, so callers shard them over contexts).  Several contexts on
+ *     several devices may live in one process (the reference is a single
+ *     process); sfm_bank_copy_peer moves packed descriptors between them.
  */
 #ifndef SFM_B200_H
 #define SFM_B200_H
@@ -35,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SFM_B200_ABI_VERSION 1
+#define SFM_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SFM_API __attribute__((visibility("default")))
@@ -62,6 +64,7 @@ enum {
 };
 
 typedef struct sfm_ctx sfm_ctx;
+typedef struct sfm_ba_problem sfm_ba_problem;
 
 /* Layout-identical to cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}
  * so a result buffer can be memcpy'd into a std::vector<cv::DMatch>. */
@@ -127,6 +130,37 @@ SFM_API int sfm_upload_descriptors_async(sfm_ctx* ctx, int n_img, const void* co
 SFM_API int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* desc_u8,
                                const int32_t* n_desc, int bytes);
 
+/* ---- sharded upload: N GPUs, every image crosses PCIe once ---------------
+ *
+ * match_features_for_all has no cross-pair state (NViewReconstuct.cpp:857-870), so pairs are
+ * sharded over GPUs; every GPU needs the whole descriptor bank, but it only has to come from
+ * the host once: GPU g uploads (and validates, packs to u8) its slice of the images, and the
+ * packed 128-byte rows travel GPU to GPU over NVLink -- with an all-gather on the caller's side
+ * (one process per GPU: sfm_bank_rows_dev gives the buffer, e.g. ncclAllGather in place) or
+ * with sfm_bank_copy_peer (one process, several contexts).
+ *
+ *   sfm_bank_layout(ctx, n_img, n_desc, 128)          same on every GPU: allocates, no data
+ *   sfm_bank_upload_range(ctx, first, n, desc, 4)     this GPU's images, host -> bank
+ *   <exchange the row ranges of the other images>     NCCL / sfm_bank_copy_peer
+ *   sfm_bank_commit(ctx, first2, n2)                  images that arrived from a peer: norms,
+ *                                                     keys, |row|^2 range check
+ * The bank is usable (sfm_match_pairs*) once every image was uploaded or committed. */
+SFM_API int sfm_bank_layout(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim);
+/* desc[k] = host rows of image first_img + k (elem_bytes 4: CV_32F, 1: CV_8U); synchronous. */
+SFM_API int sfm_bank_upload_range(sfm_ctx* ctx, int first_img, int n_img, const void* const* desc,
+                                  int elem_bytes);
+SFM_API int sfm_bank_commit(sfm_ctx* ctx, int first_img, int n_img);
+/* Rows [row0, row0 + rows) of the bank belong to image img (rows = count padded to 256; rows
+ * of consecutive images are contiguous). */
+SFM_API int sfm_bank_image_rows(const sfm_ctx* ctx, int img, int64_t* row0, int64_t* rows);
+/* DEVICE pointer to the packed bank, uint8 [n_rows][128] (valid until the next layout /
+ * upload); NULL before sfm_bank_layout. */
+SFM_API void* sfm_bank_rows_dev(sfm_ctx* ctx, int64_t* n_rows);
+/* Copies the packed rows of images [first_img, first_img + n_img) from src's bank (another
+ * context of this process, usually on another device: cudaMemcpyPeerAsync over NVLink) into
+ * dst's bank and commits them.  Both banks must have the same layout. */
+SFM_API int sfm_bank_copy_peer(sfm_ctx* dst, sfm_ctx* src, int first_img, int n_img);
+
 /* For every pair p: knnMatch(desc[pair_q[p]], desc[pair_t[p]], k=2) with NORM_L2,
  * then the reference's two filter passes (NViewReconstuct.cpp:880-908):
  *   pass 1  min_dist = min{ d0 : !(d0 > ratio*d1) }           (double compare)
@@ -147,6 +181,22 @@ SFM_API int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* 
  * out = NULL / out_cap = 0 (returns SFM_E_CAPACITY when there are matches, offsets filled),
  * allocate offsets[n_pairs] entries, then fetch -- the kNN is not recomputed. */
 SFM_API int sfm_fetch_matches(sfm_ctx* ctx, sfm_match_t* out, int64_t out_cap);
+
+/* ---- one pair sharded by QUERY ROWS over several GPUs (BASELINE config 4) --
+ *
+ * Query rows of a pair are independent in knnMatch, but min_dist of pass 1
+ * (NViewReconstuct.cpp:880-894) couples them.  sfm_match_rows_begin matches query rows
+ * [q_first[p], q_first[p] + q_count[p]) of image pair_q[p] against image pair_t[p] and returns
+ * this shard's pass-1 value per pair; the caller reduces it over the shards (minimum; one float
+ * per pair) and sfm_match_rows_finish runs pass 2 under the reduced value.  Fetch the kept
+ * matches with sfm_fetch_matches: queryIdx counts within the query image, so the shards' lists
+ * concatenated in row order ARE the list of the unsharded sfm_match_pairs call.
+ * knn_raw (nullable) receives sum_p q_count[p] rows. */
+SFM_API int sfm_match_rows_begin(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
+                                 const int32_t* q_first, const int32_t* q_count, int n_pairs,
+                                 double ratio, float* min_dist);
+SFM_API int sfm_match_rows_finish(sfm_ctx* ctx, const float* min_dist, float dist_floor,
+                                  float gate_mult, int64_t* offsets, sfm_knn2_t* knn_raw);
 
 /* Device-resident variant used to time the kernels without PCIe: runs the same
  * kernels, keeps results on the device, returns only the total number of kept
@@ -223,6 +273,23 @@ SFM_API int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const do
                             const double* pts, int64_t n_pts, const int32_t* cam_idx,
                             const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
                             double* resid, double* jac, int iters, float* ms_per_launch);
+
+/* ---- the same inside a bundle-adjustment loop ------------------------------------------
+ *
+ * bundle_adjustment() (NViewReconstuct.cpp:1162-1244) creates its residual blocks once
+ * (:1187-1211); Ceres then evaluates them per LM iteration with new extrinsics and points.
+ * sfm_ba_create uploads and range-checks (on the device) the observation tables once;
+ * sfm_ba_evaluate moves only ext (48 B / camera) and pts (24 B / point) to the device -- either
+ * may be NULL to keep the previous values -- and returns what is asked for: resid [n_obs][2],
+ * jac [n_obs][2][13] (layout of sfm_reproject_jacobians), huber_cost (see
+ * sfm_reproject_residuals), kernel_ms = CUDA-event time of the kernels.  All nullable. */
+SFM_API int sfm_ba_create(sfm_ctx* ctx, int n_cam, int64_t n_pts, const int32_t* cam_idx,
+                          const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
+                          sfm_ba_problem** out);
+SFM_API int sfm_ba_evaluate(sfm_ctx* ctx, sfm_ba_problem* problem, const double intr[4],
+                            const double* ext, const double* pts, double huber_delta,
+                            double* resid, double* jac, double* huber_cost, float* kernel_ms);
+SFM_API void sfm_ba_destroy(sfm_ctx* ctx, sfm_ba_problem* problem);
 
 /* estimate_normals(pts3d, K, normals) (NViewReconstuct.cpp:551-599, called with K = 10 at
  * :1502) with PCAFitPlane (:601-690): per point the K nearest OTHER points (brute force), the

@@ -56,6 +56,17 @@ SYMBOLS = {
     "sfm_timer_start": (_i, [_vp]),
     "sfm_timer_stop": (_i, [_vp, _pf]),
     "sfm_sync": (_i, [_vp]),
+    "sfm_bank_layout": (_i, [_vp, _i, _pi, _i]),
+    "sfm_bank_upload_range": (_i, [_vp, _i, _i, C.POINTER(_vp), _i]),
+    "sfm_bank_commit": (_i, [_vp, _i, _i]),
+    "sfm_bank_image_rows": (_i, [_vp, _i, _pi64, _pi64]),
+    "sfm_bank_rows_dev": (_vp, [_vp, _pi64]),
+    "sfm_bank_copy_peer": (_i, [_vp, _vp, _i, _i]),
+    "sfm_match_rows_begin": (_i, [_vp, _pi, _pi, _pi, _pi, _i, _d, _pf]),
+    "sfm_match_rows_finish": (_i, [_vp, _pf, _f, _f, _pi64, _vp]),
+    "sfm_ba_create": (_i, [_vp, _i, _i64, _pi, _pi, _pf, _i64, C.POINTER(_vp)]),
+    "sfm_ba_evaluate": (_i, [_vp, _vp, _pd, _pd, _pd, _d, _pd, _pd, _pd, _pf]),
+    "sfm_ba_destroy": (None, [_vp, _vp]),
 }
 
 _lib = None

@@ -143,6 +143,104 @@ class Context:
             self._check(fn(self._h, len(descs), ptrs, _ptr(n, C.c_int32), dim))
         self.n_desc = [int(x) for x in n]
 
+    # ------------------------------------------------------------------ sharded upload
+    def bank_layout(self, n_desc):
+        """Lays out the bank for len(n_desc) images without data (sfm_bank_layout): the same call
+        on every GPU; images then arrive by bank_upload_range (from this host) or from a peer
+        (all-gather into bank_rows_dev / bank_copy_peer) + bank_commit."""
+        n = np.ascontiguousarray(n_desc, np.int32)
+        self._check(self._lib.sfm_bank_layout(self._h, len(n), _ptr(n, C.c_int32), 128))
+        self.n_desc = [int(x) for x in n]
+
+    def bank_upload_range(self, first_img: int, descs):
+        """Host rows of images first_img .. first_img + len(descs) - 1 -> their bank rows."""
+        descs = [np.ascontiguousarray(d) for d in descs]
+        if not descs:
+            return
+        is_u8 = all(d.dtype == np.uint8 for d in descs)
+        if not is_u8:
+            descs = [np.ascontiguousarray(d, dtype=np.float32) for d in descs]
+        for k, d in enumerate(descs):
+            if d.ndim != 2 or d.shape != (self.n_desc[first_img + k], 128):
+                raise SfmError(_capi.SFM_E_INVALID, "descriptor matrix does not match the bank layout")
+        ptrs = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs])
+        self._check(self._lib.sfm_bank_upload_range(self._h, first_img, len(descs), ptrs,
+                                                    1 if is_u8 else 4))
+
+    def bank_commit(self, first_img: int, n_img: int):
+        self._check(self._lib.sfm_bank_commit(self._h, first_img, n_img))
+
+    def bank_image_rows(self, img: int):
+        """(first bank row, padded row count) of an image; rows of consecutive images are contiguous."""
+        r0, n = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.sfm_bank_image_rows(self._h, img, C.byref(r0), C.byref(n)))
+        return r0.value, n.value
+
+    def bank_rows_dev(self):
+        """(device pointer, rows) of the packed u8 bank [rows][128]."""
+        n = C.c_int64(0)
+        p = self._lib.sfm_bank_rows_dev(self._h, C.byref(n))
+        if not p:
+            raise SfmError(_capi.SFM_E_NOT_UPLOADED, "no bank layout")
+        return int(p), n.value
+
+    def bank_as_torch(self):
+        """The packed bank as a torch uint8 CUDA tensor [rows, 128] aliasing the library's memory
+        (for torch.distributed collectives over NVLink; torch is plumbing here, nothing more)."""
+        import torch
+        ptr, rows = self.bank_rows_dev()
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (rows, 128), "typestr": "|u1", "data": (ptr, False),
+                                        "version": 3, "strides": None}
+        return torch.as_tensor(_Wrap(), device=torch.device("cuda", self.device))
+
+    def bank_copy_peer(self, src: "Context", first_img: int, n_img: int):
+        """Packed rows of images [first_img, first_img + n_img) from another context of this
+        process (usually another GPU: cudaMemcpyPeerAsync) into this bank, committed."""
+        self._check(self._lib.sfm_bank_copy_peer(self._h, src._h, first_img, n_img))
+
+    # ------------------------------------------------------------------ query-row shards
+    def match_rows_begin(self, pairs, q_first, q_count, ratio=RATIO):
+        """Pass 1 of match_features over query rows [q_first[p], q_first[p] + q_count[p]) of every
+        pair: returns this shard's min_dist per pair (reduce with MIN over the shards)."""
+        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        pq = np.ascontiguousarray(pairs[:, 0])
+        pt = np.ascontiguousarray(pairs[:, 1])
+        qf = np.ascontiguousarray(q_first, np.int32)
+        qc = np.ascontiguousarray(q_count, np.int32)
+        if not (len(qf) == len(qc) == len(pq)):
+            raise SfmError(_capi.SFM_E_INVALID, "q_first / q_count must have one entry per pair")
+        md = np.zeros(max(len(pq), 1), np.float32)
+        self._check(self._lib.sfm_match_rows_begin(self._h, _ptr(pq, C.c_int32), _ptr(pt, C.c_int32),
+                                                   _ptr(qf, C.c_int32), _ptr(qc, C.c_int32), len(pq),
+                                                   ratio, _ptr(md, C.c_float)))
+        self._rows_counts = qc.copy()
+        return md[:len(pq)]
+
+    def match_rows_finish(self, min_dist, dist_floor=DIST_FLOOR, gate_mult=GATE_MULT, want_knn=False):
+        """Pass 2 under the reduced min_dist: returns (per-pair match arrays with image-level
+        queryIdx, knn rows per pair or None)."""
+        md = np.ascontiguousarray(min_dist, np.float32)
+        n_pairs = len(self._rows_counts)
+        offsets = np.zeros(n_pairs + 1, np.int64)
+        knn = np.zeros(max(int(self._rows_counts.sum()), 1), KNN_DTYPE) if want_knn else None
+        self._check(self._lib.sfm_match_rows_finish(self._h, _ptr(md, C.c_float), dist_floor, gate_mult,
+                                                    _ptr(offsets, C.c_int64),
+                                                    knn.ctypes.data if want_knn else None))
+        total = int(offsets[n_pairs])
+        out = np.zeros(max(total, 1), MATCH_DTYPE)
+        if total:
+            self._check(self._lib.sfm_fetch_matches(self._h, out.ctypes.data, total))
+        self.last_d2h_bytes = total * MATCH_DTYPE.itemsize + offsets.nbytes
+        knn_list = None
+        if want_knn:
+            knn_list, r = [], 0
+            for c in self._rows_counts:
+                knn_list.append(knn[r:r + int(c)])
+                r += int(c)
+        return PairLists(out[:total], offsets), knn_list
+
     def _pinned(self, name: str, nbytes: int) -> np.ndarray:
         """Grow-only pinned host arena (cudaMallocHost through the C ABI) viewed as uint8."""
         cur = self._arenas.get(name)
@@ -352,6 +450,58 @@ class Context:
         tops = C.c_double(0)
         self._check(self._lib.sfm_probe_i8_peak(self._h, iters, C.byref(tops)))
         return tops.value
+
+
+class BAProblem:
+    """The residual blocks of one bundle_adjustment() call (NViewReconstuct.cpp:1187-1211), resident
+    on the GPU: observation tables are uploaded and range-checked once; evaluate() moves only the
+    cameras and points (what changes between LM iterations)."""
+
+    def __init__(self, ctx: Context, n_cam: int, n_pts: int, cam_idx, pt_idx, obs_xy):
+        self.ctx = ctx
+        cam_idx = np.ascontiguousarray(cam_idx, np.int32)
+        pt_idx = np.ascontiguousarray(pt_idx, np.int32)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2)
+        self.n_cam, self.n_pts, self.n_obs = int(n_cam), int(n_pts), int(cam_idx.shape[0])
+        h = C.c_void_p(None)
+        ctx._check(ctx._lib.sfm_ba_create(ctx._h, self.n_cam, self.n_pts, _ptr(cam_idx, C.c_int32),
+                                          _ptr(pt_idx, C.c_int32), _ptr(obs_xy, C.c_float), self.n_obs,
+                                          C.byref(h)))
+        self._h = h
+        self.kernel_ms = 0.0
+
+    def evaluate(self, intr, ext=None, pts=None, huber_delta=4.0, want_resid=True, want_jac=False,
+                 want_cost=True):
+        """Returns (resid [n_obs,2] | None, jac [n_obs,2,13] | None, cost | None); ext / pts None
+        keeps the values of the previous evaluation."""
+        intr = np.ascontiguousarray(intr, np.float64).reshape(4)
+        pe = pp = None
+        if ext is not None:
+            ext = np.ascontiguousarray(ext, np.float64).reshape(self.n_cam, 6)
+            pe = _ptr(ext, C.c_double)
+        if pts is not None:
+            pts = np.ascontiguousarray(pts, np.float64).reshape(self.n_pts, 3)
+            pp = _ptr(pts, C.c_double)
+        resid = np.empty((self.n_obs, 2), np.float64) if want_resid else None
+        jac = np.empty((self.n_obs, 2, 13), np.float64) if want_jac else None
+        cost, ms = C.c_double(0), C.c_float(0)
+        self.ctx._check(self.ctx._lib.sfm_ba_evaluate(
+            self.ctx._h, self._h, _ptr(intr, C.c_double), pe, pp, float(huber_delta),
+            _ptr(resid, C.c_double) if want_resid else None, _ptr(jac, C.c_double) if want_jac else None,
+            C.byref(cost) if want_cost else None, C.byref(ms)))
+        self.kernel_ms = ms.value
+        return resid, jac, (cost.value if want_cost else None)
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            self.ctx._lib.sfm_ba_destroy(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------- reference-shaped API

@@ -12,8 +12,12 @@ LIB = os.path.join(HERE, "libsfm_b200.so")
 SOURCES = ["match_knn.cu", "match_hamming.cu", "match_finalize.cu", "geometry.cu", "host_io.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "shared",
 ]
+# The CUDA runtime is linked as a shared library (libcudart.so.12 of the image, or the copy a host
+# process such as torch has already loaded): the library then carries none of the runtime's own
+# symbol table, and shares streams / the primary context with its host process.
+LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _nvcc() -> str:
@@ -43,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run(cmd, check=True)
         objs.append(o)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl", "-lpthread", "-lrt"]
+        cmd = [nvcc] + LINK_FLAGS + ["-o", LIB] + objs + ["-ldl", "-lpthread", "-lrt"]
         subprocess.run(cmd, check=True)
     return LIB
 

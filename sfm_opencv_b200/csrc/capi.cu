@@ -20,13 +20,14 @@ cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
+bool knn2_mode_valid(int mode);
 // match_finalize.cu
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
                              int32_t* norm, int32_t* ckey, int32_t* gmin8, uint32_t* flags,
-                             int32_t* min_norm, cudaStream_t s);
+                             cudaStream_t s);
 cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
-                          float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
-                          int64_t* offsets, cudaStream_t s);
+                          float dist_floor, float gate_mult, const float* min_dist_in,
+                          float* min_dist, int32_t* counts, int64_t* offsets, cudaStream_t s);
 cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
                                 float dist_floor, float gate_mult, const float* min_dist,
                                 const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
@@ -50,6 +51,8 @@ cudaError_t launch_gather_matched_points(const sfm_match_t* matches, const int32
 cudaError_t launch_normals(const double* pts, int n, int K, double* normals, cudaStream_t s);
 cudaError_t launch_fp64_peak(int iters, int n_sms, double* sink, cudaStream_t s);
 cudaError_t launch_camera_table(const double* ext, int n_cam, double* cam, cudaStream_t s);
+cudaError_t launch_validate_indices(const int32_t* cam_idx, const int32_t* pt_idx, int64_t n_obs,
+                                    int n_cam, int64_t n_pts, uint32_t* flag, int n_sms, cudaStream_t s);
 cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam, double* cam,
                              double* jtab, const double* pts, const int32_t* cam_idx,
                              const int32_t* pt_idx, const float* obs_xy, int64_t n_obs,
@@ -64,7 +67,7 @@ using namespace sfm;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // sfm_create has no context to hold it
 
 struct DevBuf {
   void* p = nullptr;
@@ -114,9 +117,10 @@ struct sfm_ctx {
   EncodeTiledFn encode = nullptr;
 
   // descriptor bank (padded rows)
-  DevBuf desc, norm, ckey, gmin8, flags, stage, img_min;   // img_min: min |row|^2 per image
-  std::vector<int32_t> img_min_norm;
+  DevBuf desc, norm, ckey, gmin8, flags, stage;
   std::vector<int32_t> img_n, img_row0;
+  std::vector<uint8_t> img_ok;                 // image rows + norms + keys are in the bank
+  int imgs_missing = 0;                        // images of the current layout not yet uploaded / committed
   std::vector<int2> h_items;                   // reused host staging: (pair, first work item) per pair
   std::vector<PairDesc> h_pairs;
   DevBuf ordoff;
@@ -134,6 +138,9 @@ struct sfm_ctx {
   bool last_valid = false, last_written = false;
   int64_t last_total = 0;
   int last_n_pairs = 0;
+  // sfm_match_rows_begin .. sfm_match_rows_finish (kNN rows resident, pass 2 still open)
+  bool rows_pending = false;
+  int64_t rows_total = 0;
   double last_ratio = 0.0;
   float last_floor = 0.f, last_mult = 0.f;
   std::vector<int32_t> last_pair_q, last_pair_t;   // image ids of the last call's pairs
@@ -143,7 +150,7 @@ struct sfm_ctx {
   std::vector<int64_t> kp_off;
   bool kp_ready = false;
   // geometry scratch
-  DevBuf gjtab, gjac;
+  DevBuf gjtab, gjac, gflag;
   DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
 };
 
@@ -231,7 +238,17 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     return bail(SFM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  if (const char* m = getenv("SFM_KNN_MODE")) ctx->knn_mode = atoi(m);
+  if (const char* m = getenv("SFM_KNN_MODE")) {
+    // A/B switch of the exact epilogues (0 = unfiltered, 1 = filtered; identical results);
+    // anything else exists only in -DSFM_EXPERIMENTS builds and is refused here otherwise
+    char* end = nullptr;
+    const long v = strtol(m, &end, 10);
+    if (end == m || *end != '\0' || v < 0 || v > 255 || !knn2_mode_valid(static_cast<int>(v))) {
+      sfm_destroy(ctx);
+      return bail(SFM_E_INVALID, "SFM_KNN_MODE must be 0 or 1");
+    }
+    ctx->knn_mode = static_cast<int>(v);
+  }
   if (err) *err = SFM_OK;
   return ctx;
 }
@@ -246,8 +263,8 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_min, &ctx->pairs,
-                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->pairs,
+                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -335,29 +352,29 @@ static int finish_upload(sfm_ctx* ctx) {
   return rc;
 }
 
-static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const int32_t* n_desc,
-                         int dim, bool f32, bool async) {
-  if (!ctx) return SFM_E_INVALID;
-  if (n_img <= 0 || !desc || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
+// Lays the bank out for n_img images: row offsets, allocations, zeroed rows, tensor map.
+// No descriptor data yet: every image is "missing" until it is uploaded or committed.
+static int bank_layout(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim, cudaStream_t up) {
+  if (n_img <= 0 || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
   if (dim != kDim) return fail(ctx, SFM_E_DIM, "descriptor dimension must be 128 (SIFT)");
   CK(cudaSetDevice(ctx->device));
   if (ctx->upload_pending) {            // a previous asynchronous upload still owns the staging area
     CK(cudaStreamSynchronize(ctx->copy_stream));
     ctx->upload_pending = false;
   }
-  cudaStream_t up = async ? ctx->copy_stream : ctx->stream;
   ctx->bank_ready = false;
   ctx->last_valid = false;
+  ctx->rows_pending = false;
+  for (int i = 0; i < n_img; ++i)
+    if (n_desc[i] < 0) return fail(ctx, SFM_E_INVALID, "negative descriptor count");
   ctx->img_n.assign(n_desc, n_desc + n_img);
   ctx->img_row0.resize(n_img);
+  ctx->img_ok.assign(n_img, 0);
+  ctx->imgs_missing = n_img;
   int64_t rows = 0;
-  int32_t max_n = 0;
   for (int i = 0; i < n_img; ++i) {
-    if (n_desc[i] < 0 || (n_desc[i] > 0 && !desc[i]))
-      return fail(ctx, SFM_E_INVALID, "negative count or null descriptor pointer");
     ctx->img_row0[i] = static_cast<int32_t>(rows);
     rows += (static_cast<int64_t>(n_desc[i]) + kRowPad - 1) / kRowPad * kRowPad;
-    if (n_desc[i] > max_n) max_n = n_desc[i];
     if (rows >= (1 << 26) - kRowPad)   // kernel packs (bank row | lane << 26) into one word
       return fail(ctx, SFM_E_INVALID, "descriptor bank too large (2^26 rows)");
   }
@@ -368,7 +385,71 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
   CK(ctx->gmin8.ensure(static_cast<size_t>(rows) / 8 * 4 + 64));
   CK(ctx->flags.ensure(4));
-  CK(ctx->img_min.ensure(4 * static_cast<size_t>(n_img)));
+  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, up));
+  CK(cudaMemsetAsync(ctx->flags.p, 0, 4, up));
+  ctx->bank_binary = false;
+  return make_tmap(ctx, &ctx->tmap, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
+}
+
+static void mark_image(sfm_ctx* ctx, int i) {
+  if (!ctx->img_ok[i]) {
+    ctx->img_ok[i] = 1;
+    if (--ctx->imgs_missing == 0) ctx->bank_ready = true;
+  }
+}
+
+// Host rows of images [first, first + n) -> staging -> pack kernels, queued on `up`.
+// desc[k] belongs to image first + k.  src == nullptr rows (commit) are taken from the bank.
+static int pack_images(sfm_ctx* ctx, int first, int n, const void* const* desc, bool f32,
+                       cudaStream_t up, bool record_events) {
+  const size_t elt = f32 ? 4 : 1;
+  int32_t max_n = 0;
+  for (int k = 0; k < n; ++k) max_n = std::max(max_n, ctx->img_n[first + k]);
+  const size_t img_bytes = (static_cast<size_t>(max_n) * kDim * elt + 255) / 256 * 256;
+  if (desc) CK(ctx->stage.ensure(2 * img_bytes + 512));
+  for (int k = 0; k < n; ++k) {
+    const int i = first + k;
+    const void* src = nullptr;
+    if (desc) {
+      // alternate staging halves; copies and pack kernels are ordered by the single stream
+      uint8_t* st = ctx->stage.as<uint8_t>() + (k & 1) * img_bytes;
+      const size_t bytes = static_cast<size_t>(ctx->img_n[i]) * kDim * elt;
+      if (bytes) {
+        if (!desc[k]) return fail(ctx, SFM_E_INVALID, "null descriptor pointer");
+        CK(cudaMemcpyAsync(st, desc[k], bytes, cudaMemcpyHostToDevice, up));
+      }
+      src = st;
+    }
+    CK(launch_pack_rows(f32, src, ctx->img_n[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
+                        ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
+                        ctx->flags.as<uint32_t>(), up));
+    ctx->launches += 3;
+    if (record_events) CK(cudaEventRecord(ctx->img_ev[i], up));      // image i is resident after this
+  }
+  return SFM_OK;
+}
+
+// Reads the validation flags back (synchronously) and marks the images on success.
+static int finish_pack(sfm_ctx* ctx, int first, int n, cudaStream_t up) {
+  uint32_t flags = 0;
+  CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
+  CK(cudaStreamSynchronize(up));
+  const int rc = check_upload_flags(ctx, flags);
+  if (rc) return rc;
+  for (int k = 0; k < n; ++k) mark_image(ctx, first + k);
+  return SFM_OK;
+}
+
+static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const int32_t* n_desc,
+                         int dim, bool f32, bool async) {
+  if (!ctx) return SFM_E_INVALID;
+  if (n_img <= 0 || !desc || !n_desc) return fail(ctx, SFM_E_INVALID, "null or empty image list");
+  for (int i = 0; i < n_img; ++i)
+    if (n_desc[i] > 0 && !desc[i])
+      return fail(ctx, SFM_E_INVALID, "negative count or null descriptor pointer");
+  cudaStream_t up = async ? ctx->copy_stream : ctx->stream;
+  int rc = bank_layout(ctx, n_img, n_desc, dim, up);
+  if (rc) return rc;
   if (async) {
     while (ctx->img_ev.size() < static_cast<size_t>(n_img)) {
       cudaEvent_t e = nullptr;
@@ -376,25 +457,7 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
       ctx->img_ev.push_back(e);
     }
   }
-  CK(cudaMemsetAsync(ctx->img_min.p, 0x7f, 4 * static_cast<size_t>(n_img), up));
-  const size_t elt = f32 ? 4 : 1;
-  const size_t img_bytes = static_cast<size_t>(max_n) * kDim * elt;
-  CK(ctx->stage.ensure(2 * img_bytes + 512));
-  CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, up));
-  CK(cudaMemsetAsync(ctx->flags.p, 0, 4, up));
-  for (int i = 0; i < n_img; ++i) {
-    // alternate staging halves; copies and pack kernels are ordered by the single stream
-    uint8_t* st = ctx->stage.as<uint8_t>() + (i & 1) * ((img_bytes + 255) / 256 * 256);
-    const size_t bytes = static_cast<size_t>(n_desc[i]) * kDim * elt;
-    if (bytes) CK(cudaMemcpyAsync(st, desc[i], bytes, cudaMemcpyHostToDevice, up));
-    CK(launch_pack_rows(f32, st, n_desc[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
-                        ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
-                        ctx->flags.as<uint32_t>(), ctx->img_min.as<int32_t>() + i, up));
-    ctx->launches += 3;
-    if (async) CK(cudaEventRecord(ctx->img_ev[i], up));      // image i is resident after this
-  }
-  ctx->img_min_norm.assign(n_img, 0);
-  int rc = make_tmap(ctx, &ctx->tmap, ctx->desc.p, static_cast<uint64_t>(rows), kTileN);
+  rc = pack_images(ctx, 0, n_img, desc, f32, up, async);
   if (rc) return rc;
   if (async) {
     // return at once: sfm_match_pairs makes its kernels wait for the images they read and
@@ -402,18 +465,90 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
     CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
     CK(cudaEventRecord(ctx->upload_done, up));
     ctx->upload_pending = true;
-  } else {
-    uint32_t flags = 0;
-    CK(cudaMemcpyAsync(ctx->img_min_norm.data(), ctx->img_min.p, 4 * static_cast<size_t>(n_img),
-                       cudaMemcpyDeviceToHost, up));
-    CK(cudaMemcpyAsync(&flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
-    CK(cudaStreamSynchronize(up));
-    rc = check_upload_flags(ctx, flags);
-    if (rc) return rc;
+    for (int i = 0; i < n_img; ++i) mark_image(ctx, i);
+    return SFM_OK;
   }
-  ctx->bank_binary = false;
-  ctx->bank_ready = true;
+  return finish_pack(ctx, 0, n_img, up);
+}
+
+// ---- sharded upload: every GPU uploads a slice of the images, the packed u8 rows
+// travel GPU to GPU (NCCL all-gather on the caller's side, or sfm_bank_copy_peer) ------------
+int sfm_bank_layout(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = bank_layout(ctx, n_img, n_desc, dim, ctx->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
   return SFM_OK;
+}
+
+static int range_ok(sfm_ctx* ctx, int first_img, int n_img) {
+  if (ctx->img_n.empty() || ctx->bank_binary) return fail(ctx, SFM_E_NOT_UPLOADED, "call sfm_bank_layout first");
+  if (first_img < 0 || n_img < 0 || first_img + n_img > static_cast<int>(ctx->img_n.size()))
+    return fail(ctx, SFM_E_INVALID, "image range outside the bank layout");
+  return SFM_OK;
+}
+
+int sfm_bank_upload_range(sfm_ctx* ctx, int first_img, int n_img, const void* const* desc,
+                          int elem_bytes) {
+  if (!ctx) return SFM_E_INVALID;
+  if (elem_bytes != 4 && elem_bytes != 1)
+    return fail(ctx, SFM_E_INVALID, "elem_bytes must be 4 (CV_32F) or 1 (CV_8U)");
+  int rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (n_img == 0) return SFM_OK;
+  if (!desc) return fail(ctx, SFM_E_INVALID, "null descriptor list");
+  CK(cudaSetDevice(ctx->device));
+  rc = pack_images(ctx, first_img, n_img, desc, elem_bytes == 4, ctx->stream, false);
+  if (rc) return rc;
+  return finish_pack(ctx, first_img, n_img, ctx->stream);
+}
+
+int sfm_bank_commit(sfm_ctx* ctx, int first_img, int n_img) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (n_img == 0) return SFM_OK;
+  CK(cudaSetDevice(ctx->device));
+  rc = pack_images(ctx, first_img, n_img, nullptr, false, ctx->stream, false);
+  if (rc) return rc;
+  return finish_pack(ctx, first_img, n_img, ctx->stream);
+}
+
+int sfm_bank_image_rows(const sfm_ctx* ctx, int img, int64_t* row0, int64_t* rows) {
+  if (!ctx || img < 0 || img >= static_cast<int>(ctx->img_n.size())) return SFM_E_INVALID;
+  if (row0) *row0 = ctx->img_row0[img];
+  if (rows) *rows = (static_cast<int64_t>(ctx->img_n[img]) + kRowPad - 1) / kRowPad * kRowPad;
+  return SFM_OK;
+}
+
+void* sfm_bank_rows_dev(sfm_ctx* ctx, int64_t* n_rows) {
+  if (!ctx || ctx->img_n.empty() || ctx->bank_binary) return nullptr;
+  if (n_rows) *n_rows = ctx->bank_rows;
+  return ctx->desc.p;
+}
+
+int sfm_bank_copy_peer(sfm_ctx* dst, sfm_ctx* src, int first_img, int n_img) {
+  if (!dst || !src) return SFM_E_INVALID;
+  sfm_ctx* ctx = dst;
+  int rc = range_ok(dst, first_img, n_img);
+  if (rc) return rc;
+  if (src->img_n != dst->img_n || src->bank_binary)
+    return fail(dst, SFM_E_INVALID, "source and destination banks have different layouts");
+  if (n_img == 0) return SFM_OK;
+  for (int i = first_img; i < first_img + n_img; ++i)
+    if (!src->img_ok[i]) return fail(dst, SFM_E_NOT_UPLOADED, "source bank does not hold the image");
+  // rows of consecutive images are contiguous in the bank: one copy
+  const int last = first_img + n_img - 1;
+  const size_t off = static_cast<size_t>(dst->img_row0[first_img]) * kDim;
+  const size_t end = (static_cast<size_t>(dst->img_row0[last]) +
+                      (static_cast<size_t>(dst->img_n[last]) + kRowPad - 1) / kRowPad * kRowPad) * kDim;
+  CK(cudaSetDevice(src->device));
+  CK(cudaStreamSynchronize(src->stream));                 // the source rows are complete
+  CK(cudaSetDevice(dst->device));
+  if (end > off)
+    CK(cudaMemcpyPeerAsync(dst->desc.as<uint8_t>() + off, dst->device, src->desc.as<uint8_t>() + off,
+                           src->device, end - off, dst->stream));
+  return sfm_bank_commit(dst, first_img, n_img);
 }
 
 int sfm_upload_descriptors(sfm_ctx* ctx, int n_img, const float* const* desc_f32,
@@ -452,7 +587,9 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
   ctx->last_valid = false;
   ctx->img_n.assign(n_desc, n_desc + n_img);
   ctx->img_row0.resize(n_img);
-  ctx->img_min_norm.assign(n_img, 0);
+  ctx->img_ok.assign(n_img, 1);
+  ctx->imgs_missing = 0;
+  ctx->rows_pending = false;
   int64_t rows = 0;
   int32_t max_n = 0;
   for (int i = 0; i < n_img; ++i) {
@@ -487,11 +624,20 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
 
 // ----------------------------------------------------------------------------- matching
 // Builds the pair / work-item tables, runs kNN + filter passes, leaves results on the device.
-static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, int n_pairs,
+// q_first / q_count (nullable): pair p matches only query rows [q_first[p], q_first[p] + q_count[p])
+// of its query image (a query-row shard of one huge pair).
+static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
+                        const int32_t* q_first, const int32_t* q_count, int n_pairs,
                         double ratio, float dist_floor, float gate_mult, int64_t* total_rows,
                         bool time_it) {
   if (!ctx) return SFM_E_INVALID;
-  if (!ctx->bank_ready) return fail(ctx, SFM_E_NOT_UPLOADED, "call sfm_upload_descriptors first");
+  if (!ctx->bank_ready)
+    return fail(ctx, SFM_E_NOT_UPLOADED,
+                ctx->img_n.empty() ? "call sfm_upload_descriptors first"
+                                   : "some images of the bank layout were neither uploaded nor committed");
+  if ((q_first == nullptr) != (q_count == nullptr))
+    return fail(ctx, SFM_E_INVALID, "q_first and q_count go together");
+  ctx->rows_pending = false;
   if (n_pairs < 0 || (n_pairs > 0 && (!pair_q || !pair_t)))
     return fail(ctx, SFM_E_INVALID, "null pair list");
   CK(cudaSetDevice(ctx->device));
@@ -511,11 +657,14 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
       return fail(ctx, SFM_E_TOO_FEW_TRAIN,
                   "train image has fewer than 2 descriptors (reference reads knn[i][1])");
     PairDesc& pd = pairs[p];
-    pd.q_row0 = ctx->img_row0[q];
+    const int first = q_first ? q_first[p] : 0, count = q_first ? q_count[p] : ctx->img_n[q];
+    if (first < 0 || count < 0 || first + count > ctx->img_n[q])
+      return fail(ctx, SFM_E_INVALID, "query row range outside the query image");
+    pd.q_row0 = ctx->img_row0[q] + first;
     pd.t_row0 = ctx->img_row0[t];
-    pd.nq = ctx->img_n[q];
+    pd.nq = count;
     pd.nt = ctx->img_n[t];
-    pd.nt_min = ctx->img_min_norm[t];
+    pd.q_first = first;
     pd.pad = 0;
     pd.knn_off = rows;                          // results stay in caller order
     rows += pd.nq;
@@ -610,7 +759,7 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
   }
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
-                   gate_mult, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
+                   gate_mult, nullptr, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
                    ctx->offsets.as<int64_t>(), ctx->stream));
   ctx->launches += (n_pairs > 0 ? 2 : 1);
   return finish_upload(ctx);     // no-op unless an asynchronous upload is pending: its verdict
@@ -648,7 +797,7 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
   if (out_cap < 0 || (out_cap > 0 && !out)) return fail(ctx, SFM_E_INVALID, "bad output buffer");
   int64_t rows = 0;
   ctx->last_valid = false;
-  int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, false);
+  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, false);
   if (rc) return rc;
   CK(cudaMemcpyAsync(offsets, ctx->offsets.p, 8 * (n_pairs + 1), cudaMemcpyDeviceToHost,
                      ctx->stream));
@@ -676,6 +825,74 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
   return fetch_matches(ctx, out, out_cap);
 }
 
+// ---- one pair (or several) sharded by QUERY ROWS over GPUs -------------
+// min_dist of match_features (NViewReconstuct.cpp:880-894) couples every query row of a pair,
+// so a row shard cannot finish pass 2 on its own: begin() runs the kNN and pass 1 over this
+// shard's rows and hands back its min_dist; the caller takes the minimum over the shards (one
+// float per pair: MPI/NCCL MIN, or a host loop) and finish() runs pass 2 under that value.
+// The concatenation of the shards' match lists in row order is then exactly the list of the
+// unsharded call (queryIdx are indices within the query image).
+int sfm_match_rows_begin(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
+                         const int32_t* q_first, const int32_t* q_count, int n_pairs, double ratio,
+                         float* min_dist) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!q_first || !q_count || (n_pairs > 0 && !min_dist))
+    return fail(ctx, SFM_E_INVALID, "q_first, q_count and min_dist must not be null");
+  int64_t rows = 0;
+  ctx->last_valid = false;
+  // dist_floor / gate_mult do not enter pass 1; the counts of this launch are discarded
+  int rc = match_device(ctx, pair_q, pair_t, q_first, q_count, n_pairs, ratio, 0.f, 0.f, &rows, false);
+  if (rc) return rc;
+  if (n_pairs)
+    CK(cudaMemcpyAsync(min_dist, ctx->min_dist.p, 4 * static_cast<size_t>(n_pairs),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->last_pair_q.assign(pair_q, pair_q + n_pairs);
+  ctx->last_pair_t.assign(pair_t, pair_t + n_pairs);
+  ctx->last_n_pairs = n_pairs;
+  ctx->last_ratio = ratio;
+  ctx->rows_total = rows;
+  ctx->rows_pending = true;
+  return SFM_OK;
+}
+
+int sfm_match_rows_finish(sfm_ctx* ctx, const float* min_dist, float dist_floor, float gate_mult,
+                          int64_t* offsets, sfm_knn2_t* knn_raw) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!ctx->rows_pending) return fail(ctx, SFM_E_INVALID, "no sfm_match_rows_begin result is pending");
+  if (!offsets) return fail(ctx, SFM_E_INVALID, "offsets must not be null");
+  const int n_pairs = ctx->last_n_pairs;
+  if (n_pairs > 0 && !min_dist) return fail(ctx, SFM_E_INVALID, "min_dist must not be null");
+  CK(cudaSetDevice(ctx->device));
+  // counts / offsets under the caller's min_dist; ctx->min_dist then holds it for pass 2
+  CK(ctx->knn_f.ensure(4 * static_cast<size_t>(n_pairs) + 4));
+  if (n_pairs)
+    CK(cudaMemcpyAsync(ctx->knn_f.p, min_dist, 4 * static_cast<size_t>(n_pairs),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ctx->last_ratio,
+                   dist_floor, gate_mult, ctx->knn_f.as<float>(), ctx->min_dist.as<float>(),
+                   ctx->counts.as<int32_t>(), ctx->offsets.as<int64_t>(), ctx->stream));
+  ctx->launches += (n_pairs > 0 ? 2 : 1);
+  CK(cudaMemcpyAsync(offsets, ctx->offsets.p, 8 * (n_pairs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));                 // knn_f is reused below
+  if (knn_raw && ctx->rows_total) {
+    CK(ctx->knn_f.ensure(sizeof(sfm_knn2_t) * ctx->rows_total));
+    CK(launch_knn_to_float(ctx->knn.as<Knn2>(), ctx->rows_total, ctx->knn_f.as<sfm_knn2_t>(), ctx->stream));
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(knn_raw, ctx->knn_f.p, sizeof(sfm_knn2_t) * ctx->rows_total,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->last_total = offsets[n_pairs];
+  ctx->last_offsets.assign(offsets, offsets + n_pairs + 1);
+  ctx->last_floor = dist_floor;
+  ctx->last_mult = gate_mult;
+  ctx->last_written = false;
+  ctx->last_valid = true;
+  ctx->rows_pending = false;
+  return SFM_OK;
+}
+
 int sfm_fetch_matches(sfm_ctx* ctx, sfm_match_t* out, int64_t out_cap) {
   if (!ctx) return SFM_E_INVALID;
   if (!ctx->last_valid) return fail(ctx, SFM_E_INVALID, "no sfm_match_pairs result to fetch");
@@ -692,7 +909,7 @@ int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t*
   ctx->last_valid = false;
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  int rc = match_device(ctx, pair_q, pair_t, n_pairs, ratio, dist_floor, gate_mult, &rows, true);
+  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, true);
   if (rc) return rc;
   int64_t total = 0;
   CK(cudaMemcpyAsync(&total, ctx->offsets.as<int64_t>() + n_pairs, 8, cudaMemcpyDeviceToHost,
@@ -790,6 +1007,20 @@ int sfm_estimate_normals(sfm_ctx* ctx, const double* pts, int64_t n_pts, int K, 
   return SFM_OK;
 }
 
+// Range check of uploaded observation tables, on the device; one 4-byte read-back.
+static int check_indices(sfm_ctx* ctx, const int32_t* d_cam, const int32_t* d_pt, int64_t n_obs,
+                         int n_cam, int64_t n_pts) {
+  CK(ctx->gflag.ensure(4));
+  CK(launch_validate_indices(d_cam, d_pt, n_obs, n_cam, n_pts, ctx->gflag.as<uint32_t>(), ctx->n_sms,
+                             ctx->stream));
+  ctx->launches += 1;
+  uint32_t bad = 0;
+  CK(cudaMemcpyAsync(&bad, ctx->gflag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
+  return SFM_OK;
+}
+
 // ----------------------------------------------------------------------------- Jacobians
 int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const double* ext, int n_cam,
                             const double* pts, int64_t n_pts, const int32_t* cam_idx,
@@ -800,9 +1031,6 @@ int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const double* ex
     return fail(ctx, SFM_E_INVALID, "null camera / point tables");
   if (n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)))
     return fail(ctx, SFM_E_INVALID, "null observation arrays");
-  for (int64_t k = 0; k < n_obs; ++k)
-    if (cam_idx[k] < 0 || cam_idx[k] >= n_cam || pt_idx[k] < 0 || pt_idx[k] >= n_pts)
-      return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
   if (n_obs == 0) return SFM_OK;
   CK(cudaSetDevice(ctx->device));
   CK(ctx->gext.ensure(sizeof(double) * 6 * n_cam));
@@ -819,6 +1047,10 @@ int sfm_reproject_jacobians(sfm_ctx* ctx, const double intr[4], const double* ex
   CK(cudaMemcpyAsync(ctx->gci.p, cam_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->gpi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->gobs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const int rc = check_indices(ctx, ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), n_obs, n_cam, n_pts);
+    if (rc) return rc;
+  }
   double* dres = (resid || iters > 0) ? ctx->gres.as<double>() : nullptr;
   const int reps = iters > 0 ? iters : 1;
   auto launch = [&](bool tables) {
@@ -993,10 +1225,6 @@ static int residual_common(sfm_ctx* ctx, const double intr[4], const double* ext
     return fail(ctx, SFM_E_INVALID, "null camera / point tables");
   if (n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_xy)))
     return fail(ctx, SFM_E_INVALID, "null observation arrays");
-  for (int64_t k = 0; k < n_obs; ++k) {
-    if (cam_idx[k] < 0 || cam_idx[k] >= n_cam || pt_idx[k] < 0 || pt_idx[k] >= n_pts)
-      return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
-  }
   CK(cudaSetDevice(ctx->device));
   if (n_obs == 0) {
     if (huber_cost) *huber_cost = 0.0;
@@ -1019,6 +1247,10 @@ static int residual_common(sfm_ctx* ctx, const double intr[4], const double* ext
   CK(cudaMemcpyAsync(ctx->gci.p, cam_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->gpi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->gobs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    const int rc = check_indices(ctx, ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), n_obs, n_cam, n_pts);
+    if (rc) return rc;
+  }
   CK(launch_camera_table(ctx->gext.as<double>(), n_cam, ctx->gcam.as<double>(), ctx->stream));
   ctx->launches += 1;
   double* dres = (resid || iters > 0) ? ctx->gres.as<double>() : nullptr;
@@ -1069,6 +1301,115 @@ int sfm_reproject_residuals_timed(sfm_ctx* ctx, const double intr[4], const doub
   if (iters <= 0) return fail(ctx, SFM_E_INVALID, "iters must be positive");
   return residual_common(ctx, intr, ext, n_cam, pts, n_pts, cam_idx, pt_idx, obs_xy, n_obs,
                          huber_delta, resid, huber_cost, iters, ms_per_launch);
+}
+
+// ----------------------------------------------------------------------------- BA loop
+// bundle_adjustment() (NViewReconstuct.cpp:1162-1244) builds its residual blocks ONCE (:1187-1211)
+// and Ceres then evaluates them once or twice per LM iteration with new extrinsics / points.
+// A problem handle mirrors that: observation tables are uploaded and range-checked once and stay
+// in HBM; an evaluation moves only the 48-byte cameras and 24-byte points down and the
+// requested outputs up.
+struct sfm_ba_problem {
+  int n_cam = 0;
+  int64_t n_pts = 0, n_obs = 0;
+  int grid = 1;
+  DevBuf ci, pi, obs, ext, cam, jtab, pts, res, jac, bc, cost;
+};
+
+int sfm_ba_create(sfm_ctx* ctx, int n_cam, int64_t n_pts, const int32_t* cam_idx,
+                  const int32_t* pt_idx, const float* obs_xy, int64_t n_obs, sfm_ba_problem** out) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!out) return fail(ctx, SFM_E_INVALID, "out must not be null");
+  *out = nullptr;
+  if (n_cam <= 0 || n_pts <= 0 || n_obs <= 0 || !cam_idx || !pt_idx || !obs_xy)
+    return fail(ctx, SFM_E_INVALID, "empty problem or null observation arrays");
+  CK(cudaSetDevice(ctx->device));
+  sfm_ba_problem* pb = new sfm_ba_problem();
+  auto drop = [&](int rc) {
+    sfm_ba_destroy(ctx, pb);
+    return rc;
+  };
+  pb->n_cam = n_cam;
+  pb->n_pts = n_pts;
+  pb->n_obs = n_obs;
+  pb->grid = geometry_grid(n_obs, ctx->n_sms);
+#define CKP(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ctx->err = std::string(#call " failed: ") + cudaGetErrorString(e__);               \
+      return drop(e__ == cudaErrorMemoryAllocation ? SFM_E_NOMEM : SFM_E_CUDA);          \
+    }                                                                                    \
+  } while (0)
+  CKP(pb->ci.ensure(4 * n_obs));
+  CKP(pb->pi.ensure(4 * n_obs));
+  CKP(pb->obs.ensure(8 * n_obs));
+  CKP(pb->ext.ensure(sizeof(double) * 6 * n_cam));
+  CKP(pb->cam.ensure(sizeof(double) * 12 * n_cam));
+  CKP(pb->jtab.ensure(sizeof(double) * 8 * n_cam));
+  CKP(pb->pts.ensure(sizeof(double) * 3 * n_pts));
+  CKP(pb->res.ensure(16 * n_obs));
+  CKP(pb->bc.ensure(8 * pb->grid));
+  CKP(pb->cost.ensure(8));
+  CKP(cudaMemcpyAsync(pb->ci.p, cam_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(pb->pi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaMemcpyAsync(pb->obs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+#undef CKP
+  const int rc = check_indices(ctx, pb->ci.as<int32_t>(), pb->pi.as<int32_t>(), n_obs, n_cam, n_pts);
+  if (rc) return drop(rc);
+  *out = pb;
+  return SFM_OK;
+}
+
+void sfm_ba_destroy(sfm_ctx* ctx, sfm_ba_problem* pb) {
+  if (!pb) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  DevBuf* bufs[] = {&pb->ci, &pb->pi, &pb->obs, &pb->ext, &pb->cam, &pb->jtab, &pb->pts, &pb->res,
+                    &pb->jac, &pb->bc, &pb->cost};
+  for (DevBuf* b : bufs) b->release();
+  delete pb;
+}
+
+int sfm_ba_evaluate(sfm_ctx* ctx, sfm_ba_problem* pb, const double intr[4], const double* ext,
+                    const double* pts, double huber_delta, double* resid, double* jac,
+                    double* huber_cost, float* kernel_ms) {
+  if (!ctx) return SFM_E_INVALID;
+  if (!pb || !intr) return fail(ctx, SFM_E_INVALID, "null problem or intrinsics");
+  CK(cudaSetDevice(ctx->device));
+  // ext / pts nullable: keep the values of the previous evaluation (e.g. only points moved)
+  if (ext) CK(cudaMemcpyAsync(pb->ext.p, ext, sizeof(double) * 6 * pb->n_cam, cudaMemcpyHostToDevice, ctx->stream));
+  if (pts) CK(cudaMemcpyAsync(pb->pts.p, pts, sizeof(double) * 3 * pb->n_pts, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (jac) {
+    CK(pb->jac.ensure(sizeof(double) * 26 * static_cast<size_t>(pb->n_obs)));
+    CK(launch_jacobians(intr, pb->ext.as<double>(), pb->n_cam, pb->cam.as<double>(), pb->jtab.as<double>(),
+                        pb->pts.as<double>(), pb->ci.as<int32_t>(), pb->pi.as<int32_t>(), pb->obs.as<float>(),
+                        pb->n_obs, (resid && !huber_cost) ? pb->res.as<double>() : nullptr,
+                        pb->jac.as<double>(), ctx->n_sms, true, ctx->stream));
+    ctx->launches += 3;
+  } else {
+    CK(launch_camera_table(pb->ext.as<double>(), pb->n_cam, pb->cam.as<double>(), ctx->stream));
+    ctx->launches += 1;
+  }
+  if (huber_cost || (resid && !jac)) {
+    CK(launch_residuals(intr, pb->cam.as<double>(), pb->pts.as<double>(), pb->ci.as<int32_t>(),
+                        pb->pi.as<int32_t>(), pb->obs.as<float>(), pb->n_obs, huber_delta,
+                        resid ? pb->res.as<double>() : nullptr, huber_cost ? pb->bc.as<double>() : nullptr,
+                        pb->cost.as<double>(), pb->grid, ctx->stream));
+    ctx->launches += huber_cost ? 2 : 1;
+  }
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (resid) CK(cudaMemcpyAsync(resid, pb->res.p, 16 * pb->n_obs, cudaMemcpyDeviceToHost, ctx->stream));
+  if (jac)
+    CK(cudaMemcpyAsync(jac, pb->jac.p, sizeof(double) * 26 * static_cast<size_t>(pb->n_obs),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  if (huber_cost) CK(cudaMemcpyAsync(huber_cost, pb->cost.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev[0], ctx->ev[1]));
+  return SFM_OK;
 }
 
 // ----------------------------------------------------------------------------- probe

@@ -22,9 +22,14 @@ constexpr int kMaxViewsSmem = 64;   // projection matrices staged in shared memo
 // cv::triangulatePoints builds); the wanted vector is the right singular vector of the
 // smallest singular value = eigenvector of the smallest eigenvalue of M = A^T A (4x4, SPD).
 // adj(M) = sum_i (prod_{j != i} lambda_j) v_i v_i^T is dominated by v_4 v_4^T with relative
-// weight lambda_4/lambda_3 for the rest, so x = adj(M) e_k (k = largest diagonal cofactor)
-// followed by two more products with adj(M) converges to v_4 like (lambda_4/lambda_3)^3.
-// ~180 double FMAs per point instead of a Jacobi SVD.
+// weight rho = lambda_4/lambda_3 for the rest, so x = adj(M) e_k (k = largest diagonal cofactor)
+// followed by two more products with adj(M) converges to v_4 like rho^3: enough for consistent
+// rays (rho ~ 1e-8).  The reference also triangulates ALL matches of later pairs
+// (NViewReconstuct.cpp:1441), mismatches included, whose rays do not meet (rho up to ~0.3 on
+// the bundled data): the last product doubles as a convergence test, and the rows that fail it
+// take null_vector_slow(): adj(M) squared 14 times (rho^16384), which is the SVD answer for
+// every system whose two smallest singular values are distinguishable in float64.
+// ~190 double FMAs per point on the fast path instead of a Jacobi SVD.
 struct Sym4 {
   double m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
 };
@@ -87,6 +92,45 @@ __device__ __forceinline__ double pow2_inv(double x) {
   return (e > 0 && e < 2046) ? __hiloint2double(ne << 20, 0) : 1.0;
 }
 
+// Rows whose fast iteration has not converged (lambda_4/lambda_3 not small: noisy or mismatched
+// rays): B <- B^2 (rescaled by an exact power of two) squares the eigenvalue ratio each time.
+// (tr(B)^2 - tr(B^2)) / 2 is the sum of the principal 2x2 minors of B ~ mu_1 mu_2, so its ratio
+// to tr(B)^2 measures the current eigenvalue ratio mu_2/mu_1 of B for free: the loop stops as
+// soon as B is rank one to kTriRank (2-4 squarings for noisy inliers, at most kTriSquarings,
+// i.e. rho^16384, for rays that miss each other).  The column of the largest diagonal entry is
+// then v_4 to float64 accuracy.  Out of line: rare, and its second matrix must not cost the
+// fast path registers.
+constexpr double kTriTol = 1e-9;
+constexpr double kTriRank = 1e-12;
+constexpr int kTriSquarings = 14;
+__device__ __noinline__ void null_vector_slow(Sym4 b, double& x0, double& x1, double& x2,
+                                              double& x3) {
+  for (int k = 0; k < kTriSquarings; ++k) {
+    const double sc = pow2_inv(b.m00 + b.m11 + b.m22 + b.m33);   // trace > 0: B is PSD
+    b.m00 *= sc; b.m01 *= sc; b.m02 *= sc; b.m03 *= sc; b.m11 *= sc;
+    b.m12 *= sc; b.m13 *= sc; b.m22 *= sc; b.m23 *= sc; b.m33 *= sc;
+    Sym4 r;
+    r.m00 = b.m00 * b.m00 + b.m01 * b.m01 + b.m02 * b.m02 + b.m03 * b.m03;
+    r.m01 = b.m00 * b.m01 + b.m01 * b.m11 + b.m02 * b.m12 + b.m03 * b.m13;
+    r.m02 = b.m00 * b.m02 + b.m01 * b.m12 + b.m02 * b.m22 + b.m03 * b.m23;
+    r.m03 = b.m00 * b.m03 + b.m01 * b.m13 + b.m02 * b.m23 + b.m03 * b.m33;
+    r.m11 = b.m01 * b.m01 + b.m11 * b.m11 + b.m12 * b.m12 + b.m13 * b.m13;
+    r.m12 = b.m01 * b.m02 + b.m11 * b.m12 + b.m12 * b.m22 + b.m13 * b.m23;
+    r.m13 = b.m01 * b.m03 + b.m11 * b.m13 + b.m12 * b.m23 + b.m13 * b.m33;
+    r.m22 = b.m02 * b.m02 + b.m12 * b.m12 + b.m22 * b.m22 + b.m23 * b.m23;
+    r.m23 = b.m02 * b.m03 + b.m12 * b.m13 + b.m22 * b.m23 + b.m23 * b.m33;
+    r.m33 = b.m03 * b.m03 + b.m13 * b.m13 + b.m23 * b.m23 + b.m33 * b.m33;
+    const double tb = b.m00 + b.m11 + b.m22 + b.m33, tr = r.m00 + r.m11 + r.m22 + r.m33;
+    b = r;
+    if (tb * tb - tr <= kTriRank * tb * tb) break;               // B was already rank one
+  }
+  double best = b.m00;
+  x0 = b.m00; x1 = b.m01; x2 = b.m02; x3 = b.m03;
+  if (b.m11 > best) { best = b.m11; x0 = b.m01; x1 = b.m11; x2 = b.m12; x3 = b.m13; }
+  if (b.m22 > best) { best = b.m22; x0 = b.m02; x1 = b.m12; x2 = b.m22; x3 = b.m23; }
+  if (b.m33 > best) { best = b.m33; x0 = b.m03; x1 = b.m13; x2 = b.m23; x3 = b.m33; }
+}
+
 // Projection matrices of up to kMaxViewsParam views travel as a kernel parameter: the fp64
 // FMAs then take them straight from the constant bank (no shared-memory loads, no registers).
 constexpr int kMaxViewsParam = 8;
@@ -133,8 +177,7 @@ triangulate_kernel(const __grid_constant__ ProjParam pp, const float* __restrict
     if (fabs(adj.m11) > best) { best = fabs(adj.m11); x0 = adj.m01; x1 = adj.m11; x2 = adj.m12; x3 = adj.m13; }
     if (fabs(adj.m22) > best) { best = fabs(adj.m22); x0 = adj.m02; x1 = adj.m12; x2 = adj.m22; x3 = adj.m23; }
     if (fabs(adj.m33) > best) { best = fabs(adj.m33); x0 = adj.m03; x1 = adj.m13; x2 = adj.m23; x3 = adj.m33; }
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    {
       const double inv = pow2_inv(best);
       x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
       sym4_mul(adj, x0, x1, x2, x3);
@@ -143,6 +186,20 @@ triangulate_kernel(const __grid_constant__ ProjParam pp, const float* __restrict
     {
       const double inv = pow2_inv(best);
       x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
+      // last product = convergence test: the component of y = adj x orthogonal to x,
+      // |y|^2 |x|^2 - (x.y)^2 <= tol^2 |y|^2 |x|^2  (direction change below kTriTol)
+      double y0 = x0, y1 = x1, y2 = x2, y3 = x3;
+      sym4_mul(adj, y0, y1, y2, y3);
+      const double xx = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+      const double yy = y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
+      const double c0 = x1 * y0 - x0 * y1, c1 = x2 * y0 - x0 * y2, c2 = x3 * y0 - x0 * y3;
+      const double c3 = x2 * y1 - x1 * y2, c4 = x3 * y1 - x1 * y3, c5 = x3 * y2 - x2 * y3;
+      const double cross2 = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      if (!(cross2 <= (kTriTol * kTriTol) * xx * yy)) null_vector_slow(adj, x0, x1, x2, x3);
+      best = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(x2), fabs(x3)));
+      const double inv2 = pow2_inv(best);
+      x0 *= inv2; x1 *= inv2; x2 *= inv2; x3 *= inv2;
     }
     const double n2 = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;   // in [1, 4] after the scaling
     const double inv = n2 > 0.0 ? rsqrt(n2) : 0.0;
@@ -587,6 +644,29 @@ cudaError_t launch_triangulate(const float* P, const float* P_host, const float*
   } else {
     triangulate_kernel<false, 0><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
   }
+  return cudaGetLastError();
+}
+
+// Range check of the observation tables on the device (they are uploaded anyway): *flag != 0
+// when an observation names a camera or point that does not exist.
+__global__ void __launch_bounds__(256)
+validate_indices_kernel(const int32_t* __restrict__ cam_idx, const int32_t* __restrict__ pt_idx,
+                        int64_t n_obs, int n_cam, int64_t n_pts, uint32_t* __restrict__ flag) {
+  bool bad = false;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n_obs; k += stride) {
+    const int c = __ldg(cam_idx + k), j = __ldg(pt_idx + k);
+    bad |= (c < 0) | (c >= n_cam) | (j < 0) | (j >= n_pts);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+cudaError_t launch_validate_indices(const int32_t* cam_idx, const int32_t* pt_idx, int64_t n_obs,
+                                    int n_cam, int64_t n_pts, uint32_t* flag, int n_sms, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(flag, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  if (n_obs > 0)
+    validate_indices_kernel<<<geometry_grid(n_obs, n_sms), 256, 0, s>>>(cam_idx, pt_idx, n_obs, n_cam, n_pts, flag);
   return cudaGetLastError();
 }
 

@@ -22,11 +22,12 @@ constexpr int kMaxNorm = (1 << 21) - 1;
 
 // One warp per descriptor row. src = float rows (is_f32) or u8 rows of ONE image;
 // dst rows are in padded bank coordinates starting at row0.
-template <bool kF32>
+// kStore = false: the u8 rows are already in the bank (written by a peer copy / collective,
+// sfm_bank_commit); only their norms and keys are derived.
+template <bool kF32, bool kStore>
 __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
                                  uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
-                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags,
-                                 int32_t* __restrict__ min_norm) {
+                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -47,13 +48,13 @@ __global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
   } else {
     packed = reinterpret_cast<const uint32_t*>(src)[static_cast<size_t>(r) * 32 + lane];
   }
-  reinterpret_cast<uint32_t*>(desc)[static_cast<size_t>(row0 + r) * 32 + lane] = packed;
+  if constexpr (kStore)
+    reinterpret_cast<uint32_t*>(desc)[static_cast<size_t>(row0 + r) * 32 + lane] = packed;
   int s = __dp4a(packed, packed, 0u);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (s > kMaxNorm) bad |= kFlagNorm;
   if (lane == 0) {
-    atomicMin(min_norm, s);
     norm[row0 + r] = s;
     ckey[row0 + r] = (s << kColBits) | (r & ((1 << kColBits) - 1));
   }
@@ -91,8 +92,8 @@ __device__ __forceinline__ bool ratio_fails(float d0, float d1, double ratio) {
 // Pass 1 + count of pass 2. One block per pair.
 __global__ void __launch_bounds__(256)
 filter_count_kernel(const Knn2* __restrict__ knn, const PairDesc* __restrict__ pairs, double ratio,
-                    float dist_floor, float gate_mult, float* __restrict__ min_dist,
-                    int32_t* __restrict__ counts) {
+                    float dist_floor, float gate_mult, const float* __restrict__ min_dist_in,
+                    float* __restrict__ min_dist, int32_t* __restrict__ counts) {
   __shared__ uint32_t s_min;
   __shared__ int s_cnt;
   const PairDesc pd = pairs[blockIdx.x];
@@ -102,17 +103,21 @@ filter_count_kernel(const Knn2* __restrict__ knn, const PairDesc* __restrict__ p
     s_cnt = 0;
   }
   __syncthreads();
-  uint32_t lmin = __float_as_uint(FLT_MAX);
-  for (int i = threadIdx.x; i < pd.nq; i += blockDim.x) {
-    const int4 v = *reinterpret_cast<const int4*>(&k[i]);
-    const float d0 = __fsqrt_rn(static_cast<float>(v.z));
-    const float d1 = __fsqrt_rn(static_cast<float>(v.w));
-    if (!ratio_fails(d0, d1, ratio)) lmin = min(lmin, __float_as_uint(d0));  // d0 >= 0
+  // min_dist_in: pass 1 was done elsewhere (a pair sharded by query rows over several GPUs:
+  // min_dist couples all query rows of the pair, so it is the minimum over the shards)
+  if (min_dist_in == nullptr) {
+    uint32_t lmin = __float_as_uint(FLT_MAX);
+    for (int i = threadIdx.x; i < pd.nq; i += blockDim.x) {
+      const int4 v = *reinterpret_cast<const int4*>(&k[i]);
+      const float d0 = __fsqrt_rn(static_cast<float>(v.z));
+      const float d1 = __fsqrt_rn(static_cast<float>(v.w));
+      if (!ratio_fails(d0, d1, ratio)) lmin = min(lmin, __float_as_uint(d0));  // d0 >= 0
+    }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_min, lmin);
+    __syncthreads();
   }
-  lmin = __reduce_min_sync(0xffffffffu, lmin);
-  if ((threadIdx.x & 31) == 0) atomicMin(&s_min, lmin);
-  __syncthreads();
-  const float md = __uint_as_float(s_min);
+  const float md = min_dist_in ? min_dist_in[blockIdx.x] : __uint_as_float(s_min);
   const float gate = gate_mult * fmaxf(md, dist_floor);   // 5 * max(min_dist, 10.0f), float
   int c = 0;
   for (int i = threadIdx.x; i < pd.nq; i += blockDim.x) {
@@ -202,7 +207,7 @@ filter_write_kernel(const Knn2* __restrict__ knn, const PairDesc* __restrict__ p
     const int rank = before + __popc(ballot & ((1u << lane) - 1u));
     if (keep && off + rank < out_cap) {
       sfm_match_t m;
-      m.queryIdx = i;
+      m.queryIdx = i + pd.q_first;       // index within the query IMAGE (row shards: q_first > 0)
       m.trainIdx = v.x;
       m.imgIdx = 0;
       m.distance = d0;
@@ -252,21 +257,23 @@ cudaError_t launch_build_items(const int2* ordoff, int n_pairs, const PairDesc* 
   return cudaGetLastError();
 }
 
+// src == nullptr: derive norms / keys from the u8 rows already in the bank
 cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t* desc,
                              int32_t* norm, int32_t* ckey, int32_t* gmin8, uint32_t* flags,
-                             int32_t* min_norm, cudaStream_t s) {
+                             cudaStream_t s) {
   // 128-thread CTAs (<= 24 registers per thread): they fit next to a resident kNN CTA (768 threads,
   // 61440 of the SM's 65536 registers), so an asynchronous upload keeps packing while the
   // matching kernel owns every SM
   if (n > 0) {
     const int warps = 4;
     const int grid = (n + warps - 1) / warps;
-    if (f32)
-      pack_rows_kernel<true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags,
-                                                         min_norm);
+    if (src == nullptr)
+      pack_rows_kernel<false, false><<<grid, warps * 32, 0, s>>>(
+          desc + static_cast<size_t>(row0) * kDim, n, row0, nullptr, norm, ckey, flags);
+    else if (f32)
+      pack_rows_kernel<true, true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
     else
-      pack_rows_kernel<false><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags,
-                                                          min_norm);
+      pack_rows_kernel<false, true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
   }
   const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
   if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 127) / 128, 128, 0, s>>>(n, n_pad, row0, norm, ckey);
@@ -274,12 +281,13 @@ cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t
   return cudaGetLastError();
 }
 
+// min_dist_in == nullptr: pass 1 + count of pass 2; otherwise the count under the given min_dist
 cudaError_t launch_filter(const Knn2* knn, const PairDesc* pairs, int n_pairs, double ratio,
-                          float dist_floor, float gate_mult, float* min_dist, int32_t* counts,
-                          int64_t* offsets, cudaStream_t s) {
+                          float dist_floor, float gate_mult, const float* min_dist_in,
+                          float* min_dist, int32_t* counts, int64_t* offsets, cudaStream_t s) {
   if (n_pairs > 0)
-    filter_count_kernel<<<n_pairs, 256, 0, s>>>(knn, pairs, ratio, dist_floor, gate_mult, min_dist,
-                                                counts);
+    filter_count_kernel<<<n_pairs, 256, 0, s>>>(knn, pairs, ratio, dist_floor, gate_mult,
+                                                min_dist_in, min_dist, counts);
   scan_counts_kernel<<<1, 1024, 0, s>>>(counts, n_pairs, offsets);
   return cudaGetLastError();
 }

@@ -49,6 +49,15 @@
 
 namespace sfm {
 
+// Timing experiments (anatomy modes 2..4 and the dbg bits; their results are garbage by design)
+// exist only in -DSFM_EXPERIMENTS builds (tools/variants.py); the shipped library has the exact
+// modes 0 / 1 and nothing else.
+#ifdef SFM_EXPERIMENTS
+#define SFM_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define SFM_DBG(bit) false
+#endif
+
 #ifndef SFM_STAGES
 #define SFM_STAGES 6                            // tools/variants.py builds other depths with -D
 #endif
@@ -85,8 +94,7 @@ struct ItemInfo {
   int32_t rows_valid;   // query rows of this block that exist (<= 256)
   int32_t norm_row;     // bank row of the block's first query row
   int32_t t_row0;       // bank row of the train image's first row
-  int32_t nt_min;       // min |t|^2 over the train image
-  int32_t pad;
+  int32_t pad[2];
   int64_t knn_row;      // first output row of the block
 };
 
@@ -112,8 +120,8 @@ __device__ __forceinline__ void merge_top2(int& a1, int& a2, int b1, int b2) {
   a2 = __vimin3_s32(t, a2, b2);
 }
 
-// Packed key of accumulator r (= q.t) and column key ck = (|t|^2 << 9) | (train row & 511):
-// ((|t|^2 - 2 q.t) << 9) | column, one IMAD; orders like (distance, lower column first).
+// Packed key of accumulator r (= q.t) and column key ck = (|t|^2 << kColBits) | (train row & 1023):
+// ((|t|^2 - 2 q.t) << kColBits) | column, one IMAD; orders like (distance, lower column first).
 __device__ __forceinline__ int make_key(uint32_t r, int ck) {
   return static_cast<int>(r) * -(2 << kColBits) + ck;   // wraps, true value fits
 }
@@ -171,9 +179,6 @@ __device__ __forceinline__ void insert_vi(RowTop2& s, int v, int i) {
 
 // exact keys of the 8 columns of a group (column keys from the shared-memory ring) -> (m1, m2)
 __device__ __forceinline__ void group_insert(const uint32_t* a, uint32_t ck_addr, RowTop2& s) {
-#ifdef SFM_EXP_XLAT    // timing experiment: one more dependent shared-memory round trip per hit
-  ck_addr += static_cast<uint32_t>(lds_32(ck_addr)) & 0u;
-#endif
   const int4 c0 = lds_v4(ck_addr), c1 = lds_v4(ck_addr + 16);
   int k[8];
   k[0] = make_key(a[0], c0.x); k[1] = make_key(a[1], c0.y);
@@ -217,10 +222,6 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
     const int4 nn = lds_v4(gm_addr);
     const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
     bool h[4];
-#ifdef SFM_EXP_NOVOTE   // rows that pass branch to the insert on their own (no warp vote)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
-#else
     if constexpr (kPreVote) {
       bool p[4];
 #pragma unroll
@@ -233,37 +234,12 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t c
       for (int j = 0; j < 4; ++j)
         h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
     }
-#endif
-#ifdef SFM_EXP_XVOTE   // timing experiment: 4 more votes per chunk (vote.all next to vote.any)
-    {
-      bool v = false;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v |= __all_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
-      if (v) s.g1i ^= 1;     // all 32 rows pass at once: practically never after the first tiles
-    }
-#endif
-#ifdef SFM_EXP_XFAST   // timing experiment: 4 more independent ALU ops per chunk in the fast path
-    {
-      int x0 = s.g1i, x1 = s.g2i, x2 = s.g1i, x3 = s.g2i;
-      asm volatile("max.s32 %0, %0, %4;\n\tmax.s32 %1, %1, %5;\n\tmax.s32 %2, %2, %6;\n\tmax.s32 %3, %3, %7;"
-                   : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3) : "r"(n8[0]), "r"(n8[1]), "r"(n8[2]), "r"(n8[3]));
-      if ((x0 ^ x1 ^ x2 ^ x3) == 0x12345677) s.g1i = x0;
-    }
-#endif
     mid();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (h[j]) {
         group_insert(&r[8 * j], ck_addr + 32 * j, s);
         s.bv = min(s.bv, s.m2 >> kColBits);
-#ifdef SFM_EXP_XALU    // timing experiment: 8 more dependent ALU ops per hit (no effect on values)
-        {
-          int x = s.bv;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) asm volatile("max.s32 %0, %0, %1;" : "+r"(x) : "r"(s.bv - q - 1));
-          s.bv = x;
-        }
-#endif
       }
     }
   }
@@ -319,7 +295,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_a_full(b), 1);
       // every MMA warp + every epilogue warp
-      mbar_init(bar_a_empty(b), (dbg & 2) ? kMmaWarps : kMmaWarps + kEpiWarps);
+      mbar_init(bar_a_empty(b), SFM_DBG(2) ? kMmaWarps : kMmaWarps + kEpiWarps);
     }
     for (int b = 0; b < kAccBufs; ++b)
       for (int h = 0; h < 2; ++h) {
@@ -328,9 +304,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       }
     fence_mbar_init();
   }
-  if (threadIdx.x < kTileM)    // (item tag, second-best value) slots of the row-sharing threads
+  if (threadIdx.x < kTileM)    // tagged (best, second best) slots of the row-sharing threads
     for (int h = 0; h < 2; ++h)
-      sts_v4(smem_base + kOffShare + threadIdx.x * 32 + h * 16, 0xffffffffu, 0, 0, 0);
+      sts_v2(smem_base + kOffShare + threadIdx.x * 32 + h * 16, 0xffffffffu, 0xffffffffu);
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -364,7 +340,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           info[abuf].rows_valid = pd.nq - mblk * kTileM;
           info[abuf].norm_row = pd.q_row0 + mblk * kTileM;
           info[abuf].t_row0 = pd.t_row0;
-          info[abuf].nt_min = pd.nt_min;
           info[abuf].knn_row = pd.knn_off + static_cast<int64_t>(mblk) * kTileM;
           mbar_arrive_expect_tx(bar_a_full(abuf), kABytes);
           tma_load_2d(sA + abuf * kABytes, &tmap, bar_a_full(abuf), 0, pd.q_row0 + mblk * kTileM);
@@ -384,7 +359,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           mbar_wait(bar_empty(stage), phase ^ 1);
           const int row = t_row0 + t * kTileN;
           if (elect_one()) {
-            if (dbg & 1) {                       // timing experiment: no operand traffic
+            if (SFM_DBG(1)) {                    // timing experiment: no operand traffic
               mbar_arrive(bar_full(stage));
             } else {
               mbar_arrive_expect_tx(bar_full(stage), kBBytes + kCkBytes + kGmBytes);
@@ -425,7 +400,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         for (; ts < end; ts += 2) {
           const uint32_t stage = ts % kStages;
           mbar_wait(bar_full(stage), (ts / kStages) & 1);
-          if (!(dbg & 2)) mbar_wait(bar_t_empty(mp, mh), ((ts >> 1) & 1) ^ 1);
+          if (!SFM_DBG(2)) mbar_wait(bar_t_empty(mp, mh), ((ts >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint64_t b_desc = make_smem_desc_sw128(sB + stage * kBBytes);
           if (elect_one()) {
@@ -463,7 +438,6 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     int neg2 = -2;
     asm volatile("" : "+r"(t_addr), "+r"(bar_tf), "+r"(bar_te), "+r"(ck_base), "+r"(gm_base),
                  "+r"(neg2));
-#ifndef SFM_EXP_NOUNIFORM
     // warp-uniform by construction (functions of the warp index): a broadcast lets ptxas see
     // it and keep the address arithmetic of the tile loop on the uniform datapath
     t_addr = __shfl_sync(0xffffffffu, t_addr, 0);
@@ -471,13 +445,12 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     bar_te = __shfl_sync(0xffffffffu, bar_te, 0);
     ck_base = __shfl_sync(0xffffffffu, ck_base, 0);
     gm_base = __shfl_sync(0xffffffffu, gm_base, 0);
-#endif
     const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
     const uint32_t share_own = smem_base + kOffShare + row_in_blk * 32 + chalf * 16;
     const uint32_t share_other = smem_base + kOffShare + row_in_blk * 32 + (chalf ^ 1) * 16;
     const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
-    uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0;
-    for (int item = blockIdx.x; item < n_items && !(dbg & 2); item += gridDim.x) {
+    uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0, item_seq = 0;
+    for (int item = blockIdx.x; item < n_items && !SFM_DBG(2); item += gridDim.x) {
       RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
       int ntiles = 1, rows_valid = 0, norm_row = 0;
       int64_t knn_row = 0;
@@ -487,9 +460,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         mbar_wait(bar_tf + 16 * buf, bphase);
         tc_fence_after();
         ntiles = info[abuf].ntiles;
-#ifndef SFM_EXP_NOUNIFORM
         ntiles = __shfl_sync(0xffffffffu, ntiles, 0);
-#endif
         rows_valid = info[abuf].rows_valid;
         norm_row = info[abuf].norm_row;
         knn_row = info[abuf].knn_row;
@@ -551,11 +522,18 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             if (kMode == 1) {
               // the row's second best over BOTH column halves bounds what can still enter:
               // second smallest of {own best, own second, partner's best, partner's second}
-              sts_v4(share_own, item, st.g1v, st.g2v, 0);
-              const int4 o = lds_v4(share_other);   // any earlier value of this item is valid
-              if (o.x == item) {
-                const int joint = min(max(st.g1v, o.y), o.z);
-                if (joint < (1 << 21)) bound = min(bound, joint + 1);
+              // Each 32-bit word carries its own tag (this CTA's item counter, 10 bits), so the
+              // exchange needs neither a barrier nor an atomic 8-byte access: a word of an older
+              // item, or a pair torn between two items, fails the tag test and is ignored (the
+              // partner is never more than one item away: bar.sync at every item end).  Values
+              // are < 2^21 in magnitude (a missing second best is clamped to 2^21 - 1).
+              constexpr int kNone = (1 << 21) - 1;
+              const int tag = static_cast<int>(item_seq & 1023u);
+              sts_v2(share_own, min(st.g1v, kNone) * 1024 + tag, min(st.g2v, kNone) * 1024 + tag);
+              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
+              if (((o.x & 1023) == tag) & ((o.y & 1023) == tag)) {
+                const int joint = min(max(st.g1v, o.x >> 10), o.y >> 10);
+                if (joint < kNone) bound = min(bound, joint + 1);
               }
             }
             st.bv = bound;
@@ -571,6 +549,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         if (ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, cold, ntiles);
         else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, cold, ntiles);
       } else {
+#ifdef SFM_EXPERIMENTS
         // ---- timing experiments only (results are garbage):
         // 2 = drain TMEM, 3 = handshake only, 4 = drain + max tree + compare
         for (int t = 0; t < ntiles; ++t) {
@@ -610,7 +589,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             bphase ^= 1;
           }
         }
+#endif
       }
+      ++item_seq;
       // merge the two column halves of the row: the upper half hands its top-2 over
       const uint32_t slot = merge_addr + mslot * (kTileM * 16);
       mslot ^= 1;
@@ -724,49 +705,47 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int variant)
 // -------------------------------------------------------------------------------------
 // host-side launchers (called from capi.cu)
 
-// mode 0: unfiltered exact top-2 epilogue; mode 1: threshold-filtered (default, same results)
+// mode 0: unfiltered exact top-2 epilogue; mode 1: threshold-filtered (default, same results).
+// The shared-memory opt-in is a per-device attribute of the kernel: it is set on every launch
+// (a host-side table lookup), so contexts on several devices -- one per host thread, as
+// INTEGRATION.md recommends -- each get it.
+template <int kMode>
+static cudaError_t launch_knn2_mode(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* gmin8,
+                                    const int32_t* norm, const PairDesc* pairs, const int2* items,
+                                    int n_items, Knn2* knn_out, int grid, int dbg, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(knn2_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kKnnSmemBytes);
+  if (e != cudaSuccess) return e;
+  knn2_kernel<kMode><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
+                                                                   n_items, knn_out, dbg);
+  return cudaGetLastError();
+}
+
+bool knn2_mode_valid(int mode) {
+#ifdef SFM_EXPERIMENTS
+  return (mode & 15) >= 0 && (mode & 15) <= 4 && (mode >> 4) >= 0 && (mode >> 4) <= 3;
+#else
+  return mode == 0 || mode == 1;
+#endif
+}
+
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
                         int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream) {
-  const int dbg = mode >> 4;   // timing experiments (results invalid), see tools/exp_modes.py
-  mode &= 15;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(knn2_kernel<0>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(knn2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(knn2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(knn2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kKnnSmemBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (!knn2_mode_valid(mode)) return cudaErrorInvalidValue;
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
-  if (mode == 4)
-    knn2_kernel<4><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  else if (mode == 2)
-    knn2_kernel<2><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  else if (mode == 3)
-    knn2_kernel<3><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  else if (mode == 0)
-    knn2_kernel<0><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  else
-    knn2_kernel<1><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                 n_items, knn_out, dbg);
-  return cudaGetLastError();
+#ifdef SFM_EXPERIMENTS
+  const int dbg = mode >> 4;   // timing experiments (results invalid), see tools/exp_modes.py
+  mode &= 15;
+  if (mode == 4) return launch_knn2_mode<4>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+  if (mode == 3) return launch_knn2_mode<3>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+  if (mode == 2) return launch_knn2_mode<2>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+#else
+  const int dbg = 0;
+#endif
+  if (mode == 0) return launch_knn2_mode<0>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+  return launch_knn2_mode<1>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
 }
 
 // iters > 0: 128x256x32 MMAs; iters < 0: -(n << 4 | variant): the same work as 128x128x32

@@ -16,11 +16,11 @@ constexpr int kNormPad = 0x1FFFFF; // norm^2 sentinel of padding rows: >= every 
 
 // One image pair of sfm_match_pairs.
 struct PairDesc {
-  int32_t q_row0;    // first bank row of the query image (padded bank coordinates)
+  int32_t q_row0;    // bank row of the first query row (padded bank coordinates)
   int32_t t_row0;    // first bank row of the train image
   int32_t nq;        // query descriptors
   int32_t nt;        // train descriptors
-  int32_t nt_min;    // min |t|^2 over the train image (bound used by the epilogue filter)
+  int32_t q_first;   // index of the first query row within its image (> 0: a query-row shard)
   int32_t pad;
   int64_t knn_off;   // first row of this pair in the kNN result array
 };

@@ -66,7 +66,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU box.  The bound is
+// wall time on %globaltimer (kMbarTimeoutNs), not a retry count: the suspend-time hint of
+// try_wait is only a hint, and under a profiler replay, a debugger or time-slicing a healthy
+// kernel can see many short retries.
+constexpr unsigned long long kMbarTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
 #ifdef SFM_NO_TRAP
@@ -74,11 +83,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   return;
 #endif
   uint32_t spins = 0;
+  unsigned long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 16)) {
-      printf("sfm_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 1023u) == 0) {                  // look at the clock once per 1024 retries
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kMbarTimeoutNs) {
+        printf("sfm_b200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.sfm_abi_version() == 1
+    assert lib.sfm_abi_version() == 2
     assert lib.sfm_strerror(-7) == b"a pair has fewer than 2 train descriptors"
 
 

@@ -34,6 +34,31 @@ def test_n_view_vs_svd(ctx, V):
     assert G.point_rel_err(xyz, ref).max() < REL_TOL
 
 
+@pytest.mark.parametrize("V", [2, 4])
+def test_planted_mismatches(ctx, V):
+    """cv::triangulatePoints is fed mismatched rays by the reference (all matches of later pairs,
+    NViewReconstuct.cpp:1441): a quarter of the points get an unrelated observation in the last
+    view, so that the smallest singular value of their DLT system is not small.  The kernel must
+    return the SVD null vector for those too (not a fixed number of power steps)."""
+    sc = synth.scene(20000, V, seed=21 + V)
+    rng = np.random.default_rng(5)
+    bad = rng.random(20000) < 0.25
+    xy = sc["xy"].copy()
+    xy[V - 1, bad] = rng.uniform([0, 0], [3648, 2736], size=(int(bad.sum()), 2)).astype(np.float32)
+    X4, xyz = ctx.triangulate_batch(sc["P"], xy)
+    sv = np.linalg.svd(G.dlt_matrix(sc["P"], xy), compute_uv=False)
+    assert (sv[bad, 3] / sv[bad, 2]).max() > 0.3            # the case the fast path cannot do
+    if V == 2:
+        cv = G.triangulate_cv(sc["P"][0], sc["P"][1], xy[0], xy[1])
+    else:
+        cv = G.triangulate_svd(sc["P"], xy)
+    ok = (sv[:, 3] < 0.999 * sv[:, 2]) & (np.abs(cv[3]) > 1e-6)
+    assert ok.sum() > 19900
+    assert G.point_rel_err(xyz[ok], G.dehomogenize(cv)[ok]).max() < REL_TOL
+    s = np.sign((X4 * cv).sum(0))
+    assert np.abs(X4 * s - cv)[:, ok].max() < 2e-6
+
+
 def test_noiseless_points_are_recovered(ctx):
     sc = synth.scene(5000, 3, seed=5, noise_px=0.0)
     _, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
@@ -232,3 +257,55 @@ def test_normals_errors(ctx):
         ctx.estimate_normals(np.zeros((10, 3)), 10)       # needs more than K points
     with pytest.raises(sfm.SfmError):
         ctx.estimate_normals(np.zeros((100, 3)), 40)
+
+
+def test_ba_problem_handle_equals_one_shot_calls(ctx):
+    """The BA-loop form (sfm_ba_create / sfm_ba_evaluate): observation tables resident, only
+    cameras and points move per evaluation -- same residuals, Jacobians and Huber cost as the
+    one-shot entry points, also after the parameters changed (bundle_adjustment() iterates,
+    NViewReconstuct.cpp:1224)."""
+    import sfm_opencv_b200 as sfm
+    sc = synth.scene(6000, 3, seed=17)
+    cam, pt = synth.observations_camera_major(6000, 3)
+    obs = sc["xy"].reshape(-1, 2)
+    pb = sfm.BAProblem(ctx, 3, 6000, cam, pt, obs)
+    rng = np.random.default_rng(1)
+    ext, X = sc["ext"].copy(), sc["X"].copy()
+    for it in range(3):
+        r, J, cost = pb.evaluate(sc["intr"], ext, X, want_jac=True)
+        r1, c1 = ctx.reproject_residuals(sc["intr"], ext, X, cam, pt, obs)
+        _, J1 = ctx.reproject_jacobians(sc["intr"], ext, X, cam, pt, obs, want_resid=False)
+        assert np.array_equal(r, r1) and np.array_equal(J, J1) and cost == c1
+        assert _resid_close(r, G.reproject_residuals(sc["intr"], ext, X, cam, pt, obs))
+        if it < 2:
+            ext[1:] += rng.normal(0, 1e-3, ext[1:].shape)
+            X += rng.normal(0, 1e-3, X.shape)
+    # only the points move: the handle keeps the cameras of the previous evaluation
+    X2 = X + 0.01
+    r2, _, c2 = pb.evaluate(sc["intr"], None, X2)
+    r3, c3 = ctx.reproject_residuals(sc["intr"], ext, X2, cam, pt, obs)
+    assert np.array_equal(r2, r3) and c2 == c3
+    # cost only (what an LM step-acceptance test needs): nothing but 8 bytes comes back
+    _, _, c4 = pb.evaluate(sc["intr"], None, None, want_resid=False)
+    assert c4 == c3
+    pb.close()
+
+
+def test_observation_indices_are_checked_on_the_device(ctx):
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    sc = synth.scene(100, 2, seed=2)
+    cam, pt = synth.observations_camera_major(100, 2)
+    obs = sc["xy"].reshape(-1, 2)
+    for bad_cam, bad_pt in ((2, 0), (-1, 0), (0, 100), (0, -5)):
+        c2, p2 = cam.copy(), pt.copy()
+        c2[57], p2[57] = bad_cam, bad_pt
+        with pytest.raises(sfm.SfmError) as e:
+            ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], c2, p2, obs)
+        assert e.value.code == _capi.SFM_E_INVALID
+        with pytest.raises(sfm.SfmError) as e:
+            ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], c2, p2, obs)
+        assert e.value.code == _capi.SFM_E_INVALID
+        with pytest.raises(sfm.SfmError) as e:
+            sfm.BAProblem(ctx, 2, 100, c2, p2, obs)
+        assert e.value.code == _capi.SFM_E_INVALID

@@ -381,17 +381,116 @@ def test_async_upload_reports_validation_errors_at_match(ctx):
 
 
 def test_one_pair_sharded_by_query_rows(ctx):
-    """BASELINE config 4 across GPUs: each rank takes a query-row range of the one pair, the
-    train set is replicated, the kNN rows concatenate (emulated here with one context)."""
+    """BASELINE config 4 across GPUs: each rank takes a query-row range of the
+    one pair, the train set is replicated.  min_dist of pass 1 (NViewReconstuct.cpp:880-894)
+    couples all query rows, so the shards exchange one float (MIN) between pass 1 and pass 2; the
+    concatenated MATCH LISTS then equal the unsharded call bit for bit (emulated with one context,
+    the shards one after the other)."""
     from sfm_opencv_b200.sharding import shard_query_rows
     q = synth.sift_like(3000, 501)
     t = synth.sift_like(5000, 502)
     t[:700] = q[1000:1700]
+    t[4000] = q[5]                       # the global min_dist (0) lives in shard 0 only
     ctx.upload_descriptors([q, t])
-    _, _, whole = ctx.match_pairs([(0, 1)], want_knn=True)
-    parts = []
-    for lo, hi in shard_query_rows(len(q), 3):
-        ctx.upload_descriptors([q[lo:hi], t])
-        _, _, k = ctx.match_pairs([(0, 1)], want_knn=True)
-        parts.append(k[0])
-    assert np.array_equal(np.concatenate(parts), whole[0])
+    wm, wmd, whole = ctx.match_pairs([(0, 1)], want_knn=True)
+    shards = shard_query_rows(len(q), 3)
+    local_md = [ctx.match_rows_begin([(0, 1)], [lo], [hi - lo])[0] for lo, hi in shards]
+    assert len(set(np.float32(x).tobytes() for x in local_md)) > 1       # the shards disagree
+    md = np.min(np.array(local_md, np.float32))
+    assert _bits(md) == _bits(wmd[0])
+    parts, knn_parts = [], []
+    for lo, hi in shards:
+        ctx.match_rows_begin([(0, 1)], [lo], [hi - lo])
+        m, k = ctx.match_rows_finish([md], want_knn=True)
+        parts.append(m[0].copy())
+        knn_parts.append(k[0])
+    assert np.array_equal(np.concatenate(knn_parts), whole[0])
+    got = np.concatenate(parts)
+    assert got.tobytes() == wm[0].tobytes() and len(got) > 500
+    # without the exchange a shard's own min_dist gives a different (wrong) gate
+    ctx.match_rows_begin([(0, 1)], [shards[2][0]], [shards[2][1] - shards[2][0]])
+    m_wrong, _ = ctx.match_rows_finish([local_md[2]])
+    assert local_md[2] > md
+
+
+def test_row_shard_errors(ctx):
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    bank = synth.image_bank(2, 300, seed0=4)
+    ctx.upload_descriptors(bank)
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.match_rows_begin([(0, 1)], [200], [200])          # beyond the query image
+    assert e.value.code == _capi.SFM_E_INVALID
+    ctx.match_pairs([(0, 1)])
+    with pytest.raises(sfm.SfmError) as e:                    # nothing pending
+        ctx._rows_counts = np.array([300], np.int32)
+        ctx.match_rows_finish([1.0])
+    assert e.value.code == _capi.SFM_E_INVALID
+
+
+def _match_bytes(c, pairs):
+    m, md, knn = c.match_pairs(pairs, want_knn=True)
+    return b"".join(x.tobytes() for x in m), md.tobytes(), b"".join(k.tobytes() for k in knn)
+
+
+def test_sharded_upload_equals_whole_upload(ctx):
+    """every GPU uploads a slice of the images, the packed rows travel GPU to GPU
+    (here: two contexts on cuda:0 and sfm_bank_copy_peer), then every context matches its pair
+    shard.  Results equal the plain upload bit for bit."""
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    from sfm_opencv_b200.sharding import shard_pairs
+    sizes = [700, 1, 513, 256, 300, 1100]
+    bank = [synth.sift_like(n, 40 + k) for k, n in enumerate(sizes)]
+    bank[3][:100] = bank[0][:100]
+    pairs = M.all_pairs(len(bank))
+    ctx.upload_descriptors(bank)
+    want = _match_bytes(ctx, [p for p in pairs if sizes[p[1]] >= 2])
+    ok_pairs = [p for p in pairs if sizes[p[1]] >= 2]
+    with sfm.Context(0) as a, sfm.Context(0) as b:
+        for c in (a, b):
+            c.bank_layout(sizes)
+        a.bank_upload_range(0, [x.astype(np.float32) for x in bank[:3]])
+        b.bank_upload_range(3, bank[3:])                       # u8 rows on this side
+        with pytest.raises(sfm.SfmError) as e:                 # half a bank is not a bank
+            a.match_pairs(ok_pairs)
+        assert e.value.code == _capi.SFM_E_NOT_UPLOADED
+        a.bank_copy_peer(b, 3, 3)
+        b.bank_copy_peer(a, 0, 3)
+        (s0, e0), (s1, e1) = shard_pairs(ok_pairs, sizes, 2)
+        ma = a.match_pairs(ok_pairs[s0:e0], want_knn=True)
+        mb = b.match_pairs(ok_pairs[s1:e1], want_knn=True)
+        got = tuple(x + y for x, y in zip((b"".join(v.tobytes() for v in ma[0]), ma[1].tobytes(),
+                                           b"".join(k.tobytes() for k in ma[2])),
+                                          (b"".join(v.tobytes() for v in mb[0]), mb[1].tobytes(),
+                                           b"".join(k.tobytes() for k in mb[2]))))
+        assert got == want
+
+
+def test_two_devices_in_one_process():
+    """One context per device in ONE process (the reference is a single process): both get their
+    own shared-memory opt-in for the kNN kernel, banks are exchanged over NVLink
+    (cudaMemcpyPeerAsync) and each device matches its shard."""
+    import ctypes
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200.sharding import shard_pairs
+    try:
+        c1 = sfm.Context(1)
+    except sfm.SfmError:
+        pytest.skip("needs two GPUs")
+    with sfm.Context(0) as c0, c1:
+        bank = synth.image_bank(6, 1500, seed0=70)
+        sizes = [len(x) for x in bank]
+        pairs = M.all_pairs(6)
+        c0.upload_descriptors(bank)
+        want = _match_bytes(c0, pairs)
+        for c in (c0, c1):
+            c.bank_layout(sizes)
+        c0.bank_upload_range(0, [x.astype(np.float32) for x in bank[:3]])
+        c1.bank_upload_range(3, [x.astype(np.float32) for x in bank[3:]])
+        c0.bank_copy_peer(c1, 3, 3)
+        c1.bank_copy_peer(c0, 0, 3)
+        (s0, e0), (s1, e1) = shard_pairs(pairs, sizes, 2)
+        got0 = _match_bytes(c0, pairs[s0:e0])
+        got1 = _match_bytes(c1, pairs[s1:e1])
+        assert tuple(x + y for x, y in zip(got0, got1)) == want

@@ -32,7 +32,7 @@ def build(specs):
                 o = os.path.join(b.CSRC, src[:-3] + ".o")
             objs.append(o)
         lib = os.path.join(VDIR, f"lib_{name}.so")
-        subprocess.run([b._nvcc(), "-shared", "-cudart", "static", "-o", lib] + objs + ["-ldl", "-lpthread", "-lrt"],
+        subprocess.run([b._nvcc()] + b.LINK_FLAGS + ["-o", lib] + objs + ["-ldl", "-lpthread", "-lrt"],
                        check=True, stderr=subprocess.DEVNULL)
         print("built", lib)
     for f in os.listdir(VDIR):
