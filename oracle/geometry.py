@@ -79,9 +79,17 @@ def triangulate_cv(P1, P2, p1, p2) -> np.ndarray:
 
 
 def dehomogenize(X4: np.ndarray) -> np.ndarray:
-    """pt /= pt(3) in float32, stored as Point3d (NViewReconstuct.cpp:1151-1156)."""
+    """``pt4d_homo /= pt4d_homo(3)`` on a ``Mat_<float>`` column, stored as Point3d
+    (NViewReconstuct.cpp:1151-1156).  OpenCV implements ``Mat_<T> /= double`` as
+    ``a.convertTo(a, -1, 1./b)`` (core/mat.inl.hpp): the reciprocal is taken in double, rounded to
+    float, and every element is multiplied by it in float32 -- NOT divided.  Pinned by the
+    reference's own bundled output: with this form 1835 of the 1847 two-view points of
+    Viewer/structure.yml are reproduced bit for bit (quotient form: 758; see
+    tests/test_oracle_geometry.py::test_dehomogenize_form_is_pinned_by_structure_yml)."""
     X4 = np.asarray(X4, np.float32)
-    xyz = (X4[:3] / X4[3:4]).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        rw = (np.float64(1.0) / X4[3].astype(np.float64)).astype(np.float32)
+    xyz = (X4[:3] * rw[None, :]).astype(np.float32)
     return np.ascontiguousarray(xyz.T).astype(np.float64)
 
 

@@ -103,8 +103,10 @@ __device__ __forceinline__ double pow2_inv(double x) {
 constexpr double kTriTol = 1e-9;
 constexpr double kTriRank = 1e-12;
 constexpr int kTriSquarings = 14;
-__device__ __noinline__ void null_vector_slow(Sym4 b, double& x0, double& x1, double& x2,
-                                              double& x3) {
+struct Vec4d {
+  double x0, x1, x2, x3;
+};
+__device__ __noinline__ Vec4d null_vector_slow(Sym4 b) {   // by value in, by value out: registers
   for (int k = 0; k < kTriSquarings; ++k) {
     const double sc = pow2_inv(b.m00 + b.m11 + b.m22 + b.m33);   // trace > 0: B is PSD
     b.m00 *= sc; b.m01 *= sc; b.m02 *= sc; b.m03 *= sc; b.m11 *= sc;
@@ -125,10 +127,11 @@ __device__ __noinline__ void null_vector_slow(Sym4 b, double& x0, double& x1, do
     if (tb * tb - tr <= kTriRank * tb * tb) break;               // B was already rank one
   }
   double best = b.m00;
-  x0 = b.m00; x1 = b.m01; x2 = b.m02; x3 = b.m03;
-  if (b.m11 > best) { best = b.m11; x0 = b.m01; x1 = b.m11; x2 = b.m12; x3 = b.m13; }
-  if (b.m22 > best) { best = b.m22; x0 = b.m02; x1 = b.m12; x2 = b.m22; x3 = b.m23; }
-  if (b.m33 > best) { best = b.m33; x0 = b.m03; x1 = b.m13; x2 = b.m23; x3 = b.m33; }
+  Vec4d v = {b.m00, b.m01, b.m02, b.m03};
+  if (b.m11 > best) { best = b.m11; v.x0 = b.m01; v.x1 = b.m11; v.x2 = b.m12; v.x3 = b.m13; }
+  if (b.m22 > best) { best = b.m22; v.x0 = b.m02; v.x1 = b.m12; v.x2 = b.m22; v.x3 = b.m23; }
+  if (b.m33 > best) { best = b.m33; v.x0 = b.m03; v.x1 = b.m13; v.x2 = b.m23; v.x3 = b.m33; }
+  return v;
 }
 
 // Projection matrices of up to kMaxViewsParam views travel as a kernel parameter: the fp64
@@ -165,44 +168,50 @@ triangulate_kernel(const __grid_constant__ ProjParam pp, const float* __restrict
       sym4_add_row(m, x * q[8] - q[0], x * q[9] - q[1], x * q[10] - q[2], x * q[11] - q[3]);
       sym4_add_row(m, y * q[8] - q[4], y * q[9] - q[5], y * q[10] - q[6], y * q[11] - q[7]);
     }
-    // scale so that cofactors (cubic in M) stay far from overflow for any pixel scale:
-    // an exact power of two built from the exponent of the trace (no division)
+    // scale so that cofactors (cubic in M) and three products with adj(M) stay far from overflow
+    // and underflow for any pixel scale: one exact power of two from the exponent of the trace
+    // (no division); after it |adj| <= 6 and nothing in between needs renormalising
     const double tr = m.m00 + m.m11 + m.m22 + m.m33;
     const double sc = pow2_inv(tr);
     m.m00 *= sc; m.m01 *= sc; m.m02 *= sc; m.m03 *= sc; m.m11 *= sc;
     m.m12 *= sc; m.m13 *= sc; m.m22 *= sc; m.m23 *= sc; m.m33 *= sc;
     const Sym4 adj = sym4_adjugate(m);
-    // column of the largest diagonal cofactor (|v4[k]| largest): no cancellation in the start
+    // column k of the largest diagonal cofactor (|v4[k]| largest): no cancellation in the start
     double x0 = adj.m00, x1 = adj.m01, x2 = adj.m02, x3 = adj.m03, best = fabs(adj.m00);
-    if (fabs(adj.m11) > best) { best = fabs(adj.m11); x0 = adj.m01; x1 = adj.m11; x2 = adj.m12; x3 = adj.m13; }
-    if (fabs(adj.m22) > best) { best = fabs(adj.m22); x0 = adj.m02; x1 = adj.m12; x2 = adj.m22; x3 = adj.m23; }
-    if (fabs(adj.m33) > best) { best = fabs(adj.m33); x0 = adj.m03; x1 = adj.m13; x2 = adj.m23; x3 = adj.m33; }
+    int k = 0;
+    if (fabs(adj.m11) > best) { best = fabs(adj.m11); k = 1; x0 = adj.m01; x1 = adj.m11; x2 = adj.m12; x3 = adj.m13; }
+    if (fabs(adj.m22) > best) { best = fabs(adj.m22); k = 2; x0 = adj.m02; x1 = adj.m12; x2 = adj.m22; x3 = adj.m23; }
+    if (fabs(adj.m33) > best) { best = fabs(adj.m33); k = 3; x0 = adj.m03; x1 = adj.m13; x2 = adj.m23; x3 = adj.m33; }
+    sym4_mul(adj, x0, x1, x2, x3);
     {
-      const double inv = pow2_inv(best);
-      x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
-      sym4_mul(adj, x0, x1, x2, x3);
-      best = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(x2), fabs(x3)));
-    }
-    {
-      const double inv = pow2_inv(best);
-      x0 *= inv; x1 *= inv; x2 *= inv; x3 *= inv;
-      // last product = convergence test: the component of y = adj x orthogonal to x,
-      // |y|^2 |x|^2 - (x.y)^2 <= tol^2 |y|^2 |x|^2  (direction change below kTriTol)
+      // last product = convergence test.  y = adj x is parallel to x iff x_k y_i - x_i y_k = 0
+      // for all i, k the component where v4 is largest (x_k y_k carries the scale):
+      // sum_i (x_k y_i - x_i y_k)^2 <= tol^2 (x_k y_k)^2 bounds the direction change by ~2 tol.
       double y0 = x0, y1 = x1, y2 = x2, y3 = x3;
       sym4_mul(adj, y0, y1, y2, y3);
-      const double xx = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
-      const double yy = y0 * y0 + y1 * y1 + y2 * y2 + y3 * y3;
-      const double c0 = x1 * y0 - x0 * y1, c1 = x2 * y0 - x0 * y2, c2 = x3 * y0 - x0 * y3;
-      const double c3 = x2 * y1 - x1 * y2, c4 = x3 * y1 - x1 * y3, c5 = x3 * y2 - x2 * y3;
-      const double cross2 = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5;
+      const double xk = k == 0 ? x0 : (k == 1 ? x1 : (k == 2 ? x2 : x3));
+      const double yk = k == 0 ? y0 : (k == 1 ? y1 : (k == 2 ? y2 : y3));
+      const double c0 = xk * y0 - x0 * yk, c1 = xk * y1 - x1 * yk;
+      const double c2 = xk * y2 - x2 * yk, c3 = xk * y3 - x3 * yk;
+      const double cross2 = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+      const double ref = kTriTol * xk * yk;
       x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-      if (!(cross2 <= (kTriTol * kTriTol) * xx * yy)) null_vector_slow(adj, x0, x1, x2, x3);
-      best = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(x2), fabs(x3)));
-      const double inv2 = pow2_inv(best);
-      x0 *= inv2; x1 *= inv2; x2 *= inv2; x3 *= inv2;
+      if (!(cross2 <= ref * ref)) {
+        const Vec4d v = null_vector_slow(adj);
+        x0 = v.x0; x1 = v.x1; x2 = v.x2; x3 = v.x3;
+      }
     }
+    best = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(x2), fabs(x3)));
+    const double inv2 = pow2_inv(best);
+    x0 *= inv2; x1 *= inv2; x2 *= inv2; x3 *= inv2;
     const double n2 = x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;   // in [1, 4] after the scaling
-    const double inv = n2 > 0.0 ? rsqrt(n2) : 0.0;
+    // 1/sqrt(n2): float seed + one Newton step in double (2^-22 -> 2^-43: the result is rounded to
+    // float anyway); a zero vector (degenerate input) stays zero
+    double inv = 0.0;
+    if (n2 > 0.0) {
+      const double r0 = static_cast<double>(rsqrtf(static_cast<float>(n2)));
+      inv = r0 * (1.5 - 0.5 * n2 * r0 * r0);
+    }
     // cv::triangulatePoints returns the points' dtype: float32 (pts2d are Point2f, :1147)
     const float f0 = static_cast<float>(x0 * inv), f1 = static_cast<float>(x1 * inv);
     const float f2 = static_cast<float>(x2 * inv), f3 = static_cast<float>(x3 * inv);
@@ -213,10 +222,15 @@ triangulate_kernel(const __grid_constant__ ProjParam pp, const float* __restrict
       __stcs(X4 + 3 * n_pts + i, f3);
     }
     if (xyz != nullptr) {
-      // pt4d_homo /= pt4d_homo(3) in float32, then Point3f -> Point3d (:1153-1155)
-      __stcs(xyz + 3 * i + 0, static_cast<double>(f0 / f3));
-      __stcs(xyz + 3 * i + 1, static_cast<double>(f1 / f3));
-      __stcs(xyz + 3 * i + 2, static_cast<double>(f2 / f3));
+      // pt4d_homo /= pt4d_homo(3) (:1154) on a Mat_<float> is OpenCV's a.convertTo(a, -1, 1./b):
+      // every element is MULTIPLIED by float(1.0 / w), not divided by w (this form reproduces
+      // 1835 of the 1847 two-view points of the bundled Viewer/structure.yml bit for bit, the
+      // quotient form 758); then Point3f -> Point3d (:1155).  __frcp_rn(w) = RN_float(1/w) equals
+      // float(RN_double(1/w)) except when 1/w lies within 2^-54 of a float rounding boundary.
+      const float rw = __frcp_rn(f3);
+      __stcs(xyz + 3 * i + 0, static_cast<double>(f0 * rw));
+      __stcs(xyz + 3 * i + 1, static_cast<double>(f1 * rw));
+      __stcs(xyz + 3 * i + 2, static_cast<double>(f2 * rw));
     }
   }
 }

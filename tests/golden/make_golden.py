@@ -98,7 +98,66 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"{name}_sift.npz"), **out)
 
 
+def knn_digest(dist, idx) -> np.ndarray:
+    """sha256 over the raw kNN rows (idx int32 [n,2] then dist float32 [n,2]) as 32 uint8: lets a
+    fixture pin EVERY kNN row of a large pair without storing 16 bytes per query."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(idx, np.int32).tobytes())
+    h.update(np.ascontiguousarray(dist, np.float32).tobytes())
+    return np.frombuffer(h.digest(), np.uint8).copy()
+
+
+def main_dog():
+    """dataset/dog (16 images, 4.6k-21.8k SIFT descriptors each): descriptors + keypoints, and
+    for the 15 consecutive pairs the filtered match list, min_dist and a digest of all kNN rows."""
+    name = "dog"
+    files, descs, kps = sift_dataset(name)
+    out = {"n_img": np.int32(len(descs))}
+    for i, d in enumerate(descs):
+        out[f"desc_{i}"] = d                                 # keypoints are not needed for matching
+    for i in range(len(descs) - 1):
+        dist, idx = M.knn2_cv(descs[i].astype(np.float32), descs[i + 1].astype(np.float32))
+        m, d0, md = M.filter_matches(dist, idx)
+        out[f"knn_sha_{i}"] = knn_digest(dist, idx)
+        out[f"match_{i}"] = m
+        out[f"match_dist_{i}"] = d0
+        out[f"min_dist_{i}"] = np.float32(md)
+        print(name, "pair", i, "matches", len(m), "min_dist", md, "tie rows",
+              int((dist[:, 0] == dist[:, 1]).sum()), flush=True)
+    np.savez_compressed(os.path.join(OUT, f"{name}_sift.npz"), **out)
+
+
+def main_all_pairs():
+    """Exhaustive pair lists (i < j; north_star's schedule) on the two small bundled datasets:
+    match list + kNN digest per pair from the reference's library call (descriptors are already
+    in <name>_sift.npz)."""
+    for name in ("crazyhorse", "desktop"):
+        g = np.load(os.path.join(OUT, f"{name}_sift.npz"))
+        n = int(g["n_img"])
+        out = {}
+        p = 0
+        for a in range(n):
+            for b in range(a + 1, n):
+                dist, idx = M.knn2_cv(g[f"desc_{a}"].astype(np.float32), g[f"desc_{b}"].astype(np.float32))
+                m, d0, md = M.filter_matches(dist, idx)
+                out[f"pair_{p}"] = np.array([a, b], np.int32)
+                out[f"knn_sha_{p}"] = knn_digest(dist, idx)
+                out[f"match_{p}"] = m
+                out[f"match_dist_{p}"] = d0
+                out[f"min_dist_{p}"] = np.float32(md)
+                p += 1
+        out["n_pairs"] = np.int32(p)
+        print(name, "all pairs", p, flush=True)
+        np.savez_compressed(os.path.join(OUT, f"{name}_allpairs.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--akaze-only" not in sys.argv:
-        main()
-    main_akaze()
+    if "--dog" in sys.argv:
+        main_dog()
+    elif "--all-pairs" in sys.argv:
+        main_all_pairs()
+    else:
+        if "--akaze-only" not in sys.argv:
+            main()
+        main_akaze()

@@ -1,0 +1,113 @@
+"""GPU parity on every bundled dataset (north_star: bit-exact kNN-ratio matches "on all bundled
+datasets") and property tests of the kNN-2 kernel, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import matching as M
+from test_oracle_matching import descriptor_pair, knn_sha
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _knn_arrays(k):
+    idx = np.stack([k["trainIdx0"], k["trainIdx1"]], 1)
+    dist = np.stack([k["distance0"], k["distance1"]], 1)
+    return dist, idx
+
+
+def test_dog_consecutive_pairs(ctx, golden):
+    """dataset/dog: 16 images of 4.6k-21.8k SIFT descriptors, 15 consecutive pairs
+    (match_features_for_all, NViewReconstuct.cpp:857-870): every kNN row (digest) and every match
+    list equal what the reference's library call produced (tests/golden/make_golden.py --dog)."""
+    g = golden("dog")
+    n = int(g["n_img"])
+    ctx.upload_descriptors([g[f"desc_{i}"] for i in range(n)])
+    m, md, knn = ctx.match_pairs(M.consecutive_pairs(n), want_knn=True)
+    for i in range(n - 1):
+        assert knn_sha(*_knn_arrays(knn[i])) == g[f"knn_sha_{i}"].tobytes(), f"pair {i}"
+        assert np.array_equal(m[i]["queryIdx"], g[f"match_{i}"][:, 0])
+        assert np.array_equal(m[i]["trainIdx"], g[f"match_{i}"][:, 1])
+        assert np.array_equal(_bits(m[i]["distance"]), _bits(g[f"match_dist_{i}"]))
+        assert _bits(md[i]) == _bits(g[f"min_dist_{i}"])
+
+
+@pytest.mark.parametrize("name", ["crazyhorse", "desktop"])
+def test_real_datasets_all_pairs(ctx, golden, name):
+    """The exhaustive i < j schedule (BASELINE config 3's) on real descriptor sets of very
+    different sizes (desktop: 16717 ... 838) in ONE call."""
+    g = golden(name)
+    ap = golden(name, "allpairs")
+    n = int(g["n_img"])
+    ctx.upload_descriptors([g[f"desc_{i}"] for i in range(n)])
+    pairs = [tuple(int(x) for x in ap[f"pair_{p}"]) for p in range(int(ap["n_pairs"]))]
+    assert pairs == M.all_pairs(n)
+    m, md, knn = ctx.match_pairs(pairs, want_knn=True)
+    for p in range(len(pairs)):
+        assert knn_sha(*_knn_arrays(knn[p])) == ap[f"knn_sha_{p}"].tobytes(), f"pair {pairs[p]}"
+        assert np.array_equal(m[p]["queryIdx"], ap[f"match_{p}"][:, 0])
+        assert np.array_equal(m[p]["trainIdx"], ap[f"match_{p}"][:, 1])
+        assert np.array_equal(_bits(m[p]["distance"]), _bits(ap[f"match_dist_{p}"]))
+        assert _bits(md[p]) == _bits(ap[f"min_dist_{p}"])
+
+
+# ---- property tests -------------------------------------------------------------------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+
+
+@settings(max_examples=50, deadline=None,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(descriptor_pair(max_q=300, max_t=700))
+def test_property_kernel_equals_oracle(ctx, qt):
+    """Random sizes (not multiples of any tile), duplicate rows (ties on d0 == d1), zero rows,
+    saturated 255 rows, sparse and tiny-valued descriptors."""
+    q, t = qt
+    ctx.upload_descriptors([q, t])
+    m, md, knn = ctx.match_pairs([(0, 1)], want_knn=True)
+    d, idx = M.knn2_int(q, t)
+    dist, gi = _knn_arrays(knn[0])
+    assert np.array_equal(gi, idx) and np.array_equal(_bits(dist), _bits(d))
+    om, od, omd = M.filter_matches(d, idx)
+    assert np.array_equal(m[0]["queryIdx"], om[:, 0]) and np.array_equal(m[0]["trainIdx"], om[:, 1])
+    assert np.array_equal(_bits(m[0]["distance"]), _bits(od)) and _bits(md[0]) == _bits(omd)
+
+
+@settings(max_examples=20, deadline=None,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(descriptor_pair(max_q=200, max_t=2600))
+def test_property_long_train_sets(ctx, qt):
+    """Train sets longer than one packed-key window (1024 columns): window merge + joint bound."""
+    q, t = qt
+    ctx.upload_descriptors([q, t])
+    _, _, knn = ctx.match_pairs([(0, 1)], want_knn=True)
+    d, idx = M.knn2_int(q, t)
+    dist, gi = _knn_arrays(knn[0])
+    assert np.array_equal(gi, idx) and np.array_equal(_bits(dist), _bits(d))
+
+
+def test_max_norm_rows_and_rejected_rows(ctx):
+    """|row|^2 must stay below 2^21 (float sqrt injective on the distances): the largest legal
+    rows match exactly, one more unit is SFM_E_RANGE -- an error, not a slow path."""
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    rng = np.random.default_rng(8)
+    t = np.zeros((300, 128), np.uint8)
+    for r in range(300):
+        cols = rng.choice(128, 32, replace=False)
+        t[r, cols] = 255                                # 32 * 255^2 = 2 080 800 < 2^21 = 2 097 152
+        t[r, rng.integers(0, 128)] = rng.integers(0, 100)
+    q = t[::3].copy()
+    ctx.upload_descriptors([q, t])
+    m, md, knn = ctx.match_pairs([(0, 1)], want_knn=True)
+    d, idx = M.knn2_int(q, t)
+    dist, gi = _knn_arrays(knn[0])
+    assert np.array_equal(gi, idx) and np.array_equal(_bits(dist), _bits(d))
+    bad = t.copy()
+    bad[5, :] = 0
+    bad[5, :33] = 255                                   # 33 * 255^2 > 2^21
+    with pytest.raises(sfm.SfmError) as e:
+        ctx.upload_descriptors([q, bad])
+    assert e.value.code == _capi.SFM_E_RANGE

@@ -100,3 +100,90 @@ def test_golden_fixture_pins_oracle(golden, name, expect):
         assert np.array_equal(m, g[f"match_{i}"]) and md == g[f"min_dist_{i}"]
     if name == "desktop":
         assert abs(float(g["min_dist_0"]) - 18.330) < 1e-3
+
+
+def knn_sha(dist, idx) -> bytes:
+    """The digest tests/golden/make_golden.py::knn_digest stores for large pairs."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(idx, np.int32).tobytes())
+    h.update(np.ascontiguousarray(dist, np.float32).tobytes())
+    return h.digest()
+
+
+def test_dog_fixture_pins_oracle(golden):
+    """dataset/dog (16 images; the largest bundled descriptor sets): the fixture holds the output of
+    the reference's library call for all 15 consecutive pairs as match lists + a digest of every
+    kNN row; the integer oracle reproduces the four cheapest pairs here (the GPU suite does all)."""
+    g = golden("dog")
+    sizes = [g[f"desc_{i}"].shape[0] for i in range(16)]
+    assert sizes == [17176, 16794, 19092, 14916, 4596, 21408, 17623, 21531, 14034, 21813, 15312,
+                     21436, 8644, 5112, 14509, 8688]                    # SURVEY.md section 4 item 3
+    for i in (3, 4, 12, 13):
+        d, idx = M.knn2_int(g[f"desc_{i}"], g[f"desc_{i + 1}"])
+        assert knn_sha(d, idx) == g[f"knn_sha_{i}"].tobytes()
+        m, d0, md = M.filter_matches(d, idx)
+        assert np.array_equal(m, g[f"match_{i}"]) and md == g[f"min_dist_{i}"]
+        assert np.array_equal(_bits(d0), _bits(g[f"match_dist_{i}"]))
+
+
+def test_all_pairs_fixture_pins_oracle(golden):
+    """Exhaustive (i < j) schedule on dataset/crazyhorse: 21 pairs from the reference's library
+    call; the integer oracle agrees on every one of them."""
+    g = golden("crazyhorse")
+    ap = golden("crazyhorse", "allpairs")
+    assert int(ap["n_pairs"]) == 21
+    for p in range(21):
+        a, b = ap[f"pair_{p}"]
+        d, idx = M.knn2_int(g[f"desc_{a}"], g[f"desc_{b}"])
+        assert knn_sha(d, idx) == ap[f"knn_sha_{p}"].tobytes()
+        m, _, md = M.filter_matches(d, idx)
+        assert np.array_equal(m, ap[f"match_{p}"]) and md == ap[f"min_dist_{p}"]
+
+
+# ---- property tests (SURVEY.md section 4 item 4): integer restatement == the library call -----
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def descriptor_pair(draw, max_q=40, max_t=70):
+    """(query, train) uint8 sets with planted duplicates (exact ties on d0 == d1), rows of 255s,
+    zero rows and near-duplicates -- the cases the tie-break and the packed keys must survive."""
+    nq = draw(st.integers(1, max_q))
+    nt = draw(st.integers(2, max_t))
+    seed = draw(st.integers(0, 2**31 - 1))
+    rng = np.random.default_rng(seed)
+    kind = draw(st.sampled_from(["sift", "sparse", "tiny"]))
+    if kind == "sift":
+        q, t = synth.sift_like(nq, seed % 9973), synth.sift_like(nt, seed % 9973 + 1)
+    elif kind == "sparse":
+        q = (rng.random((nq, 128)) < 0.1).astype(np.uint8) * rng.integers(0, 120, (nq, 128)).astype(np.uint8)
+        t = (rng.random((nt, 128)) < 0.1).astype(np.uint8) * rng.integers(0, 120, (nt, 128)).astype(np.uint8)
+    else:
+        q = rng.integers(0, 3, (nq, 128)).astype(np.uint8)
+        t = rng.integers(0, 3, (nt, 128)).astype(np.uint8)
+    for _ in range(draw(st.integers(0, 6))):          # duplicate train rows / copy query rows in
+        a, b = rng.integers(0, nt, 2)
+        t[a] = t[b]
+    for _ in range(draw(st.integers(0, 4))):
+        t[rng.integers(0, nt)] = q[rng.integers(0, nq)]
+    if draw(st.booleans()):
+        t[rng.integers(0, nt)] = 0
+    if draw(st.booleans()):
+        # a saturated row: 64 x 255 keeps |row|^2 = 4 161 600 > 2^21 out, 30 x 255 stays legal
+        r = np.zeros(128, np.uint8)
+        r[rng.choice(128, 30, replace=False)] = 255
+        t[rng.integers(0, nt)] = r
+        q[rng.integers(0, nq)] = r
+    return q, t
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(descriptor_pair())
+def test_property_int_oracle_equals_library(qt):
+    q, t = qt
+    d, i = M.knn2_int(q, t)
+    dc, ic = M.knn2_cv(q, t)
+    assert np.array_equal(i, ic) and np.array_equal(_bits(d), _bits(dc))
+    # order = (distance, lower index): never a later equal-distance row in front
+    assert ((d[:, 0] < d[:, 1]) | ((d[:, 0] == d[:, 1]) & (i[:, 0] < i[:, 1]))).all()
