@@ -13,7 +13,15 @@ fixed by the config, so the scaling label is "strong".
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with descriptors resident in HBM;
 `e2e` = pairs/s through the reference-facing call (host CV_32F descriptor matrices in,
-host DMatch lists out, copies inside the timed region).
+host DMatch lists out, copies inside the timed region).  With N > 1 ranks every image crosses
+PCIe once: rank r uploads its 1/N slice of the images, and the packed u8 rows are all-gathered
+over NVLink (NCCL) straight into every rank's bank (sfm_bank_layout / _upload_range / _commit).
+
+Other workloads (their own metric; lines kept under profiles/):
+    --workload pair65536   BASELINE config 4: one 65536 x 65536 pair, query rows sharded over the
+                           ranks, min_dist reduced across ranks (MIN) between pass 1 and pass 2
+    --workload geometry    BASELINE config 5: 4M points x V views, DLT triangulation + reprojection
+                           residuals, points / observations sharded over the ranks, Huber cost summed
 """
 from __future__ import annotations
 
@@ -172,70 +180,154 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------- extras
-def extras(ctx, hbm_gbs, peak_src):
-    """Secondary roofline lines (BASELINE.json configs 4 and 5), rank 0 at N=1 only."""
+def _roof(bytes_, ms, hbm_gbs, peak_src, **kw):
+    gbs = bytes_ / (ms * 1e-3) / 1e9
+    return dict({"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                 "peak_source": peak_src}, **kw)
+
+
+def extra_pair65536(ctx, n=65536, cpu=True):
+    """BASELINE config 4 on one GPU: device-resident kernel time, end to end through host buffers,
+    the reference's library call on a 4096-row query subset (parity + CPU time)."""
+    from oracle import matching as M
+    from oracle import synth
+    q = synth.sift_like(n, 1000)
+    t = synth.sift_like(n, 1001)
+    ctx.upload_descriptors([q, t])
+    ctx.match_pairs_resident([(0, 1)])
+    best = min(ctx.match_pairs_resident([(0, 1)])[1] for _ in range(5))
+    ops = 2.0 * n * n * 128
+    out = {"knn_ms": best, "tops": ops / (best * 1e-3) / 1e12,
+           "frac_of_4500": ops / (best * 1e-3) / 1e12 / INT8_DENSE_TOPS}
+    hq = ctx.pinned_empty(q.shape, np.float32, "p65q"); hq[...] = q
+    ht = ctx.pinned_empty(t.shape, np.float32, "p65t"); ht[...] = t
+    for _ in range(2):
+        ctx.upload_descriptors([hq, ht], overlap=True)
+        ctx.match_pairs([(0, 1)], copy=False)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        ctx.upload_descriptors([hq, ht], overlap=True)
+        m, md, _ = ctx.match_pairs([(0, 1)], copy=False)
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    out["e2e"] = {"ms": e2e_ms, "tops": ops / (e2e_ms * 1e-3) / 1e12, "h2d_bytes": hq.nbytes + ht.nbytes,
+                  "d2h_bytes": ctx.last_d2h_bytes, "matches": int(len(m[0])),
+                  "api": "sfm_upload_descriptors_async(CV_32F) + sfm_match_pairs + sfm_fetch_matches"}
+    if cpu:
+        import cv2
+        rows = np.sort(np.random.default_rng(0).choice(n, 4096, replace=False))
+        tf = t.astype(np.float32)
+        qf = q[rows].astype(np.float32)
+        t0 = time.perf_counter()
+        dist, idx = M.knn2_cv(qf, tf)
+        dt = time.perf_counter() - t0
+        _, _, knn = ctx.match_pairs([(0, 1)], want_knn=True)
+        k = knn[0][rows]
+        same = bool(np.array_equal(k["trainIdx0"], idx[:, 0]) and np.array_equal(k["trainIdx1"], idx[:, 1]) and
+                    np.array_equal(k["distance0"].view(np.uint32), dist[:, 0].view(np.uint32)) and
+                    np.array_equal(k["distance1"].view(np.uint32), dist[:, 1].view(np.uint32)))
+        out["parity"] = {"rows": 4096, "bit_exact_vs_cv2": same}
+        out["cpu_baseline"] = {"ms_per_pair": dt * (n / 4096) * 1e3, "cores": cv2.getNumThreads(), "kind": "reference",
+                               "sample": f"4096 of {n} query rows x {n} train rows in {dt:.2f} s, "
+                                         f"cv2 {cv2.__version__} batchDistance(K=2,NORM_L2), extrapolated x{n // 4096}"}
+    return out
+
+
+def extra_geometry(ctx, hbm_gbs, peak_src, fp64_peak, n=4_000_000, views=(2, 8), cpu=True):
+    """BASELINE config 5 on one GPU: kernel rooflines (inputs resident), end to end through host
+    buffers, the BA-loop form, and the reference's CPU calls on bounded samples."""
+    import sfm_opencv_b200 as sfm
+    from oracle import geometry as G
     from oracle import synth
     out = {}
+    for V in views:
+        sc = synth.scene(n, V)
+        _, _, ms = ctx.triangulate_batch(sc["P"], sc["xy"], want_X4=True, want_xyz=False, iters=20)
+        b = (8 * V + 16) * n
+        tri = {"ms": ms, "points_per_s": n / (ms * 1e-3),
+               "roofline": _roof(b, ms, hbm_gbs, peak_src, bytes_per_point=8 * V + 16)}
+        if fp64_peak:
+            # the kernel's real ceiling: 191 + 28 V fp64-pipe instructions per point (SASS census of
+            # triangulate_kernel, DESIGN.md 4.3), each counted like the probe's DFMA (2 flop)
+            fl = 2.0 * (191 + 28 * V) * n / (ms * 1e-3) / 1e12
+            tri["fp64"] = {"achieved_tflops": fl, "peak_tflops": fp64_peak, "frac": fl / fp64_peak,
+                           "note": "fp64-pipe bound; peak = in-run DFMA probe"}
+        t0 = time.perf_counter()
+        X4, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
+        dt = time.perf_counter() - t0
+        tri["e2e"] = {"ms": dt * 1e3, "points_per_s": n / dt, "h2d_bytes": int(sc["xy"].nbytes + sc["P"].nbytes),
+                      "d2h_bytes": int(X4.nbytes + xyz.nbytes),
+                      "api": "sfm_triangulate_batch(host xy -> host X4 + xyz), pageable numpy buffers"}
+        cam, pt = synth.observations_camera_major(n, V)
+        obs = sc["xy"].reshape(-1, 2)
+        _, _, ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs, want_cost=False, iters=20)
+        b = 32 * n * V + 24 * n
+        res = {"ms": ms, "obs_per_s": n * V / (ms * 1e-3),
+               "roofline": _roof(b, ms, hbm_gbs, peak_src, bytes_per_obs=32, bytes_per_point=24)}
+        t0 = time.perf_counter()
+        r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
+        dt = time.perf_counter() - t0
+        res["e2e"] = {"ms": dt * 1e3, "obs_per_s": n * V / dt,
+                      "h2d_bytes": int(sc["X"].nbytes + cam.nbytes + pt.nbytes + obs.nbytes),
+                      "d2h_bytes": int(r.nbytes) + 8, "api": "sfm_reproject_residuals (all tables from the host every call)"}
+        # the BA-loop form: tables resident, per evaluation only cameras + points down, cost (8 B) up
+        pb = sfm.BAProblem(ctx, V, n, cam, pt, obs)
+        pb.evaluate(sc["intr"], sc["ext"], sc["X"], want_resid=False)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            _, _, c2 = pb.evaluate(sc["intr"], sc["ext"], sc["X"], want_resid=False)
+        dt = (time.perf_counter() - t0) / 5
+        res["e2e_ba_loop"] = {"ms": dt * 1e3, "obs_per_s": n * V / dt, "kernel_ms": pb.kernel_ms,
+                              "h2d_bytes": int(sc["X"].nbytes + sc["ext"].nbytes), "d2h_bytes": 8,
+                              "cost_equals_one_shot": bool(c2 == cost),
+                              "api": "sfm_ba_create once; sfm_ba_evaluate(ext, pts) -> Huber cost"}
+        pb.close()
+        if V == 2:
+            _, _, ms = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt, obs, want_resid=False, iters=10)
+            b = (16 + 16 + 208) * n * V + 24 * n
+            out["jacobians_4M_v2"] = {"ms": ms, "obs_per_s": n * V / (ms * 1e-3),
+                                      "roofline": _roof(b, ms, hbm_gbs, peak_src, bytes_per_obs=240, bytes_per_point=24)}
+        if cpu and V == 2:
+            import cv2
+            k = 400_000
+            t0 = time.perf_counter()
+            cv = G.triangulate_cv(sc["P"][0], sc["P"][1], sc["xy"][0, :k], sc["xy"][1, :k])
+            ref = G.dehomogenize(cv)
+            dt = time.perf_counter() - t0
+            err = G.point_rel_err(xyz[:k], ref)
+            tri["cpu_baseline"] = {"points_per_s": k / dt, "cores": 1, "kind": "reference",
+                                   "sample": f"cv2 {cv2.__version__} triangulatePoints + de-homogenise on {k} of {n} points in {dt:.1f} s"}
+            tri["parity"] = {"points": k, "max_rel_err_vs_cv2": float(err.max()), "tolerance": 1e-5}
+            k = 2_000_000
+            t0 = time.perf_counter()
+            rr = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam[:k], pt[:k], obs[:k])
+            dt = time.perf_counter() - t0
+            res["cpu_baseline"] = {"obs_per_s": k / dt, "cores": 1, "kind": "port",
+                                   "sample": f"numpy fp64 restatement of ReprojectCost on {k} of {n * V} observations in {dt:.1f} s"}
+            res["parity"] = {"observations": k, "max_abs_err_px": float(np.abs(r[:k] - rr).max())}
+        out[f"triangulate_4M_v{V}"] = tri
+        out[f"residuals_4M_v{V}"] = res
+        del sc
+    return out
+
+
+def extras(ctx, hbm_gbs, peak_src, cpu=True):
+    """Secondary lines (BASELINE.json configs 4 and 5, HAMMING2), rank 0 at N=1 only."""
+    out = {}
     try:
-        q = synth.sift_like(65536, 1000)
-        t = synth.sift_like(65536, 1001)
-        ctx.upload_descriptors([q, t])
-        ctx.match_pairs_resident([(0, 1)])
-        best = min(ctx.match_pairs_resident([(0, 1)])[1] for _ in range(5))
-        ops = 2.0 * 65536 * 65536 * 128
-        out["pair_65536"] = {"knn_ms": best, "tops": ops / (best * 1e-3) / 1e12,
-                             "frac_of_4500": ops / (best * 1e-3) / 1e12 / INT8_DENSE_TOPS}
+        out["pair_65536"] = extra_pair65536(ctx, cpu=cpu)
     except Exception as e:                                   # pragma: no cover
-        out["pair_65536"] = {"error": str(e)}
+        out["pair_65536"] = {"error": repr(e)}
     try:
         fp64_peak = ctx.probe_fp64_peak(4000)                # measured DFMA rate, TFLOP/s
         out["fp64_probe_tflops"] = fp64_peak
     except Exception as e:                                   # pragma: no cover
         fp64_peak = None
-        out["fp64_probe"] = {"error": str(e)}
+        out["fp64_probe"] = {"error": repr(e)}
     try:
-        n = 4_000_000
-        for V in (2, 8):
-            sc = synth.scene(n, V)
-            _, _, ms = ctx.triangulate_batch(sc["P"], sc["xy"], want_X4=True, want_xyz=False,
-                                             iters=20)
-            b = (8 * V + 16) * n
-            out[f"triangulate_4M_v{V}"] = {
-                "ms": ms, "points_per_s": n / (ms * 1e-3),
-                "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
-                             "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
-                             "bytes_per_point": 8 * V + 16, "peak_source": peak_src}}
-            if fp64_peak:
-                # the kernel's real ceiling: ~(20 V + 170) fp64 FMA/MUL per point (DESIGN.md 4.3)
-                fl = 2.0 * (20 * V + 170) * n / (ms * 1e-3) / 1e12
-                out[f"triangulate_4M_v{V}"]["fp64"] = {"achieved_tflops": fl, "peak_tflops": fp64_peak,
-                                                       "frac": fl / fp64_peak,
-                                                       "note": "fp64-pipe bound; peak = in-run DFMA probe"}
-            cam, pt = synth.observations_camera_major(n, V)
-            _, _, ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt,
-                                               sc["xy"].reshape(-1, 2), want_cost=False,
-                                               iters=20)
-            b = 32 * n * V + 24 * n
-            out[f"residuals_4M_v{V}"] = {
-                "ms": ms, "obs_per_s": n * V / (ms * 1e-3),
-                "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
-                             "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
-                             "bytes_per_obs": 32, "bytes_per_point": 24,
-                             "peak_source": peak_src}}
-            if V == 2:
-                # Jacobians of the same residual blocks: 16 B in + 16 B residual + 208 B of
-                # derivatives per observation, 24 B per distinct point
-                _, _, ms = ctx.reproject_jacobians(sc["intr"], sc["ext"], sc["X"], cam, pt,
-                                                   sc["xy"].reshape(-1, 2), want_resid=False, iters=10)
-                b = (16 + 16 + 208) * n * V + 24 * n
-                out["jacobians_4M_v2"] = {
-                    "ms": ms, "obs_per_s": n * V / (ms * 1e-3),
-                    "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
-                                 "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_gbs,
-                                 "bytes_per_obs": 240, "bytes_per_point": 24, "peak_source": peak_src}}
-            del sc
+        out.update(extra_geometry(ctx, hbm_gbs, peak_src, fp64_peak, cpu=cpu))
     except Exception as e:                                   # pragma: no cover
-        out["geometry"] = {"error": str(e)}
+        out["geometry"] = {"error": repr(e)}
     try:
         # the live reference configuration: binary descriptors, NORM_HAMMING2 (AKAZE-sized: 61 B)
         rng = np.random.default_rng(0)
@@ -250,41 +342,105 @@ def extras(ctx, hbm_gbs, peak_src):
             "descriptor_pairs_per_s": len(pairs) * nd * nd / (best[0] * 1e-3),
             "note": "CUDA-core XOR/POPC kernel, 16 words per descriptor pair"}
     except Exception as e:                                   # pragma: no cover
-        out["hamming2"] = {"error": str(e)}
+        out["hamming2"] = {"error": repr(e)}
+    return out
+
+
+# ----------------------------------------------------------------------------- self-check
+def self_check(ctx, sfm, local_rank, bank, my_pairs, rank, world, n_oracle=16):
+    """Untimed: ties the step's output to (a) the unfiltered epilogue (SFM_KNN_MODE=0: same library,
+    every group inserted) on ALL of this rank's pairs -- match lists byte for byte, kNN rows of every
+    16th pair -- and (b) the CPU oracle (the reference's library call) on sampled pairs."""
+    import hashlib
+    out = {}
+    m1, md1, _ = ctx.match_pairs(my_pairs)
+    h1 = hashlib.sha256(m1.flat.tobytes() + m1.offsets.tobytes() + md1.tobytes()).hexdigest()
+    sub = my_pairs[::16]
+    _, _, k1 = ctx.match_pairs(sub, want_knn=True)
+    hk1 = hashlib.sha256(b"".join(k.tobytes() for k in k1)).hexdigest()
+    os.environ["SFM_KNN_MODE"] = "0"
+    try:
+        c0 = sfm.Context(local_rank)
+    finally:
+        del os.environ["SFM_KNN_MODE"]
+    c0.upload_descriptors(bank)
+    m0, md0, _ = c0.match_pairs(my_pairs)
+    h0 = hashlib.sha256(m0.flat.tobytes() + m0.offsets.tobytes() + md0.tobytes()).hexdigest()
+    _, _, k0 = c0.match_pairs(sub, want_knn=True)
+    hk0 = hashlib.sha256(b"".join(k.tobytes() for k in k0)).hexdigest()
+    c0.close()
+    out["matches_sha256"] = h1
+    out["filtered_equals_unfiltered_matches"] = bool(h1 == h0)
+    out["filtered_equals_unfiltered_knn_rows"] = bool(hk1 == hk0)
+    out["knn_rows_compared"] = int(sum(len(k) for k in k1))
+    out["pairs_compared"] = len(my_pairs)
+    if rank == 0 and n_oracle > 0:
+        from oracle import matching as M
+        rng = np.random.default_rng(123)
+        pick = sorted(rng.choice(len(my_pairs), min(n_oracle, len(my_pairs)), replace=False).tolist())
+        ok = True
+        for p in pick:
+            a, b = my_pairs[p]
+            dist, idx = M.knn2_cv(bank[a].astype(np.float32), bank[b].astype(np.float32))
+            om, od, omd = M.filter_matches(dist, idx)
+            g = m1[p]
+            ok &= bool(np.array_equal(g["queryIdx"], om[:, 0]) and np.array_equal(g["trainIdx"], om[:, 1]) and
+                       np.array_equal(g["distance"].view(np.uint32), od.view(np.uint32)) and
+                       np.float32(md1[p]).view(np.uint32) == np.float32(omd).view(np.uint32))
+        out["oracle_pairs"] = len(pick)
+        out["oracle_match_lists_equal"] = ok
     return out
 
 
 # ----------------------------------------------------------------------------- main arm
+class Ranks:
+    """torch.distributed plumbing of one rank per GPU: barrier + device sync, max / sum / min
+    over ranks (NCCL).  Nothing here is on the data path."""
+
+    def __init__(self, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+        self.torch, self.dist = torch, dist
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local_rank])
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op, dtype=None):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=dtype or self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return t.item()
+
+    def allmax(self, x):
+        return float(self._reduce(float(x), self.dist.ReduceOp.MAX))
+
+    def allsum(self, x):
+        return float(self._reduce(float(x), self.dist.ReduceOp.SUM))
+
+    def allmin_f32(self, x):
+        """Exact MIN of a float32 over the ranks (min_dist of a row-sharded pair)."""
+        return np.float32(self._reduce(float(np.float32(x)), self.dist.ReduceOp.MIN, self.torch.float32))
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
 def run_b200(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
     import sfm_opencv_b200 as sfm
     from sfm_opencv_b200.sharding import shard_pairs
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize()
-
-    def allmax(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    rk = Ranks(rank, local_rank, world)
+    torch, dist = rk.torch, rk.dist
+    barrier, allmax, allsum = rk.barrier, rk.allmax, rk.allsum
 
     ctx = sfm.Context(local_rank)
     peaks, peak_src = measured_peaks()
@@ -336,37 +492,93 @@ def run_b200(args, rank, local_rank, world):
         pass
 
     # ---- e2e: host CV_32F matrices in, host DMatch lists out, every step ----------------
-    ids = sorted({i for p in my_pairs for i in p})
-    remap = {g: k for k, g in enumerate(ids)}
-    loc_pairs = [(remap[a], remap[b]) for a, b in my_pairs]
-    host_f32 = []
-    for k, g in enumerate(ids):                              # pinned, as a caller's cv::Mat pool
-        a = ctx.pinned_empty(bank[g].shape, np.float32, f"desc{k}")
-        a[...] = bank[g]
-        host_f32.append(a)
-    h2d = sum(a.nbytes for a in host_f32) + 8 * len(loc_pairs)
+    from sfm_opencv_b200.sharding import shard_range
+    nvlink = 0
+    if world == 1:
+        host_f32 = []
+        for k in range(args.images):                         # pinned, as a caller's cv::Mat pool
+            a = ctx.pinned_empty(bank[k].shape, np.float32, f"desc{k}")
+            a[...] = bank[k]
+            host_f32.append(a)
+        h2d = sum(a.nbytes for a in host_f32) + 8 * len(my_pairs)
+        e2e_api = ("sfm_upload_descriptors_async(pinned CV_32F host matrices) + sfm_match_pairs + "
+                   "sfm_fetch_matches (host DMatch lists); every step transfers the whole bank")
+
+        def e2e_step():
+            ctx.upload_descriptors(host_f32, overlap=True)   # H2D overlaps the matching kernels
+            return ctx.match_pairs(my_pairs, copy=False)
+    else:
+        # every image crosses PCIe ONCE per step: this rank uploads images [i0, i1), the packed u8
+        # rows are all-gathered over NVLink into every rank's bank, the received images are committed
+        i0, i1 = shard_range(args.images, world)[rank]
+        host_f32 = []
+        for k in range(i0, i1):
+            a = ctx.pinned_empty(bank[k].shape, np.float32, f"desc{k}")
+            a[...] = bank[k]
+            host_f32.append(a)
+        h2d = sum(a.nbytes for a in host_f32) + 8 * len(my_pairs)
+        ctx.bank_layout(n_desc)
+        spans = []                                           # bank row range of every rank's slice
+        for r, (a0, a1) in enumerate(shard_range(args.images, world)):
+            if a1 > a0:
+                r0, _ = ctx.bank_image_rows(a0)
+                rl, nl = ctx.bank_image_rows(a1 - 1)
+                spans.append((r0, rl + nl))
+            else:
+                spans.append((0, 0))
+        equal = len({b - a for a, b in spans}) == 1 and all(spans[r][0] == r * (spans[0][1] - spans[0][0]) for r in range(world))
+        nvlink = sum(b - a for r, (a, b) in enumerate(spans) if r != rank) * 128
+        e2e_api = ("sfm_bank_layout + sfm_bank_upload_range(this rank's 1/N of the images, pinned CV_32F) + "
+                   f"NCCL {'all_gather_into_tensor (in place)' if equal else 'broadcast per rank'} of the packed u8 rows "
+                   "over NVLink + sfm_bank_commit + sfm_match_pairs + sfm_fetch_matches")
+
+        def e2e_step():
+            ctx.bank_layout(n_desc)
+            ctx.bank_upload_range(i0, host_f32)
+            bt = ctx.bank_as_torch()
+            if equal:
+                dist.all_gather_into_tensor(bt[:spans[-1][1]], bt[spans[rank][0]:spans[rank][1]])
+            else:
+                for r, (a, b) in enumerate(spans):
+                    if b > a:
+                        dist.broadcast(bt[a:b], src=r)
+            torch.cuda.current_stream().synchronize()
+            if i0 > 0:
+                ctx.bank_commit(0, i0)
+            if i1 < args.images:
+                ctx.bank_commit(i1, args.images - i1)
+            return ctx.match_pairs(my_pairs, copy=False)
+
     for _ in range(2):
-        ctx.upload_descriptors(host_f32, overlap=True)
-        ctx.match_pairs(loc_pairs, copy=False)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        ctx.upload_descriptors(host_f32, overlap=True)       # H2D overlaps the matching kernels
-        m, _, _ = ctx.match_pairs(loc_pairs, copy=False)
+        m, _, _ = e2e_step()
         d2h = ctx.last_d2h_bytes
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     barrier()
+    e2e_matches = int(allsum(len(m.flat)))
     e2e_s = allmax(e2e_s)
     e2e_val = n_pairs * args.steps / e2e_s
     h2d = int(allsum(h2d))
     d2h = int(allsum(d2h))
+    nvlink = int(allsum(nvlink))
+
+    # ---- self-check (untimed): the step's output against the unfiltered epilogue and the oracle
+    check = None
+    if not args.no_self_check:
+        ctx.upload_descriptors(bank)
+        check = self_check(ctx, sfm, local_rank, bank, my_pairs, rank, world)
+        check["e2e_matches_equal_resident"] = bool(e2e_matches == matches)
+        ok = all(v for k, v in check.items() if isinstance(v, bool))
+        check["all_ranks_ok"] = bool(allsum(0 if ok else 1) == 0)
 
     if rank != 0:
         ctx.close()
-        if world > 1:
-            dist.destroy_process_group()
+        rk.close()
         return
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload -----------
@@ -396,9 +608,8 @@ def run_b200(args, rank, local_rank, world):
         "data": "synthetic", "config": workload_config(args, world),
         "matches_per_step": matches,
         "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "sfm_upload_descriptors_async(pinned CV_32F host matrices) + sfm_match_pairs + "
-                       "sfm_fetch_matches (host DMatch lists); every step transfers the whole bank"},
+                "d2h_bytes_per_step": d2h, "nvlink_bytes_per_step": nvlink,
+                "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "knn2_kernel", "achieved": tops,
                      "peak": INT8_DENSE_TOPS, "unit": "TOP/s", "frac": tops / INT8_DENSE_TOPS,
@@ -416,12 +627,140 @@ def run_b200(args, rank, local_rank, world):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if check is not None:
+        line["self_check"] = check
     if world == 1 and not args.no_extras:
-        line["extra"] = extras(ctx, hbm_gbs, peak_src)
+        line["extra"] = extras(ctx, hbm_gbs, peak_src, cpu=not args.no_cpu_baseline)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    rk.close()
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- other workloads
+def run_pair65536(args, rank, local_rank, world):
+    """BASELINE config 4 over N GPUs: query rows of the one pair are sharded over
+    the ranks (256-row aligned), the train image is replicated, min_dist (pass 1) is reduced with
+    MIN across the ranks, pass 2 runs under the reduced value; the concatenated match lists equal
+    the single-GPU list (checked: sha256 of the gathered list vs rank 0's unsharded run)."""
+    import hashlib
+    import sfm_opencv_b200 as sfm
+    from oracle import synth
+    from sfm_opencv_b200.sharding import shard_query_rows
+    rk = Ranks(rank, local_rank, world)
+    n = args.desc if args.desc != 8192 else 65536
+    ctx = sfm.Context(local_rank)
+    q, t = synth.sift_like(n, 1000), synth.sift_like(n, 1001)
+    lo, hi = shard_query_rows(n, world)[rank]
+    hq = ctx.pinned_empty(q.shape, np.float32, "q"); hq[...] = q
+    ht = ctx.pinned_empty(t.shape, np.float32, "t"); ht[...] = t
+    ops = 2.0 * n * n * 128
+
+    def step(upload):
+        if upload:
+            ctx.upload_descriptors([hq, ht], overlap=False)
+        md_local = ctx.match_rows_begin([(0, 1)], [lo], [hi - lo])[0]
+        md = rk.allmin_f32(md_local)
+        m, _ = ctx.match_rows_finish([md])
+        return m[0], md
+
+    ctx.upload_descriptors([q, t])
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    rk.barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        m, md = step(False)
+    ms = ctx.timer_stop()
+    rk.barrier()
+    ms = rk.allmax(ms) / args.steps
+    for _ in range(2):
+        step(True)
+    rk.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m, md = step(True)
+    e2e_ms = rk.allmax(time.perf_counter() - t0) / args.steps * 1e3
+    # gathered list == unsharded list
+    from sfm_opencv_b200.sharding import gather_match_lists
+    parts = gather_match_lists([m.copy()], rank, rank + 1, world) if world > 1 else [m.copy()]
+    if rank == 0:
+        got = np.concatenate(parts)
+        ctx.upload_descriptors([q, t])
+        whole, wmd, _ = ctx.match_pairs([(0, 1)])
+        same = bool(got.tobytes() == whole[0].tobytes() and np.float32(md).tobytes() == np.float32(wmd[0]).tobytes())
+        line = {"metric": "one 65536 x 65536 SIFT pair (kNN k=2 + ratio): tera-ops/s, 2*Nq*Nt*128",
+                "value": ops / (ms * 1e-3) / 1e12, "unit": "TOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"single pair {n} x {n} x 128 (BASELINE.json configs[3]), query rows sharded "
+                                       f"over {world} rank(s), train image replicated, one float (min_dist) reduced with MIN"},
+                "frac_of_4500_per_gpu": ops / (ms * 1e-3) / 1e12 / INT8_DENSE_TOPS / world,
+                "e2e": {"value": ops / (e2e_ms * 1e-3) / 1e12, "unit": "TOP/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int((hq.nbytes + ht.nbytes) * world), "d2h_bytes_per_step": int(got.nbytes),
+                        "api": "sfm_upload_descriptors(CV_32F, both images on every rank) + sfm_match_rows_begin + "
+                               "MIN over ranks + sfm_match_rows_finish + sfm_fetch_matches"},
+                "matches": int(len(got)), "sharded_list_equals_single_gpu": same,
+                "matches_sha256": hashlib.sha256(got.tobytes()).hexdigest()}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    rk.close()
+
+
+def run_geometry(args, rank, local_rank, world):
+    """BASELINE config 5 over N GPUs: contiguous point ranges (triangulation)
+    and observation ranges (residuals) per rank, cameras replicated, no data-path collective; the
+    Huber cost is the sum of the ranks' partial costs (one double, SUM)."""
+    import sfm_opencv_b200 as sfm
+    from oracle import synth
+    from sfm_opencv_b200.sharding import shard_range
+    rk = Ranks(rank, local_rank, world)
+    ctx = sfm.Context(local_rank)
+    peaks, peak_src = measured_peaks()
+    hbm_gbs = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    n, V = args.points, args.views
+    sc = synth.scene(n, V)
+    s, e = shard_range(n, world)[rank]
+    xy = np.ascontiguousarray(sc["xy"][:, s:e])
+    cam, pt = synth.observations_camera_major(n, V)
+    # this rank's observations: every camera's view of its point range, camera-major
+    sel = np.concatenate([np.arange(v * n + s, v * n + e) for v in range(V)])
+    cam_l, pt_l, obs_l = cam[sel], pt[sel], sc["xy"].reshape(-1, 2)[sel]
+    it = 20
+    _, _, tri_ms = ctx.triangulate_batch(sc["P"], xy, want_X4=True, want_xyz=False, iters=it)
+    _, _, res_ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam_l, pt_l, obs_l, want_cost=False, iters=it)
+    rk.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        X4, xyz = ctx.triangulate_batch(sc["P"], xy)
+    tri_e2e = rk.allmax(time.perf_counter() - t0) / args.steps
+    rk.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam_l, pt_l, obs_l)
+    res_e2e = rk.allmax(time.perf_counter() - t0) / args.steps
+    tri_ms, res_ms = rk.allmax(tri_ms), rk.allmax(res_ms)
+    cost_sum = rk.allsum(cost)
+    if rank == 0:
+        _, c_all = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, sc["xy"].reshape(-1, 2),
+                                           want_resid=False)
+        line = {"metric": "points/s (batched DLT triangulation, 4M points x V views) at N GPUs",
+                "value": n / (tri_ms * 1e-3), "unit": "points/s", "n_gpus": world, "steps": it, "warmup": 1,
+                "ms_per_step": tri_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{n} points x {V} views (BASELINE.json configs[4]): contiguous point / "
+                                       f"observation ranges over {world} rank(s), cameras replicated, no collective"},
+                "roofline": _roof((8 * V + 16) * (e - s), tri_ms, hbm_gbs, peak_src, bytes_per_point=8 * V + 16, per="rank 0"),
+                "e2e": {"value": n / tri_e2e, "unit": "points/s", "ms_per_step": tri_e2e * 1e3,
+                        "h2d_bytes_per_step": int(sc["xy"].nbytes), "d2h_bytes_per_step": int(28 * n),
+                        "api": "sfm_triangulate_batch(host xy -> host X4 + xyz) on every rank's point range"},
+                "residuals": {"obs_per_s": n * V / (res_ms * 1e-3), "ms": res_ms,
+                              "roofline": _roof(32 * (e - s) * V + 24 * n, res_ms, hbm_gbs, peak_src, per="rank 0"),
+                              "e2e_obs_per_s": n * V / res_e2e, "e2e_ms": res_e2e * 1e3,
+                              "huber_cost_sum_over_ranks": cost_sum, "huber_cost_single_gpu": c_all,
+                              "rel_diff": abs(cost_sum - c_all) / abs(c_all)}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    rk.close()
 
 
 def main():
@@ -435,6 +774,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-self-check", action="store_true")
+    ap.add_argument("--workload", default="allpairs", choices=["allpairs", "pair65536", "geometry"])
+    ap.add_argument("--points", type=int, default=4_000_000)
+    ap.add_argument("--views", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -449,6 +792,10 @@ def main():
         raise SystemExit(subprocess.call(cmd + sys.argv[1:]))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "pair65536":
+        run_pair65536(args, rank, local_rank, world)
+    elif args.workload == "geometry":
+        run_geometry(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

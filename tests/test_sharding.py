@@ -117,3 +117,75 @@ def test_enumerate_observations_is_camera_major():
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     assert (np.diff(a[0]) >= 0).all() and len(a[0]) == sum(int((i >= 0).sum()) for i in ids)
+
+
+def _rows_worker(rank, world, port, q):
+    """One pair sharded by query rows with the CPU oracle as the per-rank
+    matcher: pass 1 per shard, MIN over ranks (one float), pass 2 under the reduced min_dist."""
+    import torch
+    import torch.distributed as dist
+    from oracle import matching as M
+    from oracle import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    qd, td = synth.sift_like(700, 5), synth.sift_like(900, 6)
+    td[:100] = qd[300:400]
+    td[500] = qd[3]                                  # distance 0: the global min_dist sits in shard 0
+    lo, hi = S.shard_query_rows(len(qd), world)[rank]
+    d, idx = M.knn2_int(qd[lo:hi], td)
+    _, _, md_local = M.filter_matches(d, idx)
+    t = torch.tensor([float(md_local)], dtype=torch.float32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    md = np.float32(t.item())
+    # pass 2 under the reduced value (what sfm_match_rows_finish does)
+    d0, d1 = d[:, 0], d[:, 1]
+    gate = M.GATE_MULT * max(md, M.DIST_FLOOR)
+    keep = ~((d0.astype(np.float64) > M.RATIO * d1.astype(np.float64)) | (d0 > gate))
+    out = np.zeros(int(keep.sum()), [("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+    out["queryIdx"] = np.nonzero(keep)[0] + lo
+    out["trainIdx"] = idx[keep, 0]
+    out["distance"] = d0[keep]
+    parts = S.gather_match_lists([out], rank, rank + 1, world)
+    if rank == 0:
+        q.put((float(md_local), float(md), np.concatenate(parts).tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_pair_world2_gloo_equals_unsharded():
+    import torch.multiprocessing as mp
+    from oracle import matching as M
+    from oracle import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    md_local0, md, got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    qd, td = synth.sift_like(700, 5), synth.sift_like(900, 6)
+    td[:100] = qd[300:400]
+    td[500] = qd[3]
+    m, d0, wmd = M.match_features(qd, td)[:3]
+    want = np.zeros(len(m), [("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+    want["queryIdx"], want["trainIdx"], want["distance"] = m[:, 0], m[:, 1], d0
+    assert md == float(wmd) == 0.0 and got == want.tobytes() and len(m) > 50
+
+
+def test_huber_cost_is_additive_over_observation_ranges():
+    """Residual sharding: the cost 0.5 * sum rho(|r|^2) of the whole problem is
+    the sum of the costs of contiguous observation ranges (the one scalar the ranks exchange)."""
+    from oracle import geometry as G
+    from oracle import synth
+    sc = synth.scene(3000, 3, seed=4)
+    cam, pt = synth.observations_camera_major(3000, 3)
+    r = G.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, sc["xy"].reshape(-1, 2))
+    whole = G.huber_cost(r, 4.0)
+    for world in (2, 3, 8):
+        parts = [G.huber_cost(r[s:e], 4.0) for s, e in S.shard_range(len(r), world)]
+        assert abs(sum(parts) - whole) <= 1e-12 * whole
