@@ -191,8 +191,7 @@ def extra_pair65536(ctx, n=65536, cpu=True):
     the reference's library call on a 4096-row query subset (parity + CPU time)."""
     from oracle import matching as M
     from oracle import synth
-    q = synth.sift_like(n, 1000)
-    t = synth.sift_like(n, 1001)
+    q, t = synth.image_bank(2, n, seed0=1000)             # seeds 1000 / 1001, 20 % shared rows + noise
     ctx.upload_descriptors([q, t])
     ctx.match_pairs_resident([(0, 1)])
     best = min(ctx.match_pairs_resident([(0, 1)])[1] for _ in range(5))
@@ -252,30 +251,43 @@ def extra_geometry(ctx, hbm_gbs, peak_src, fp64_peak, n=4_000_000, views=(2, 8),
             fl = 2.0 * (191 + 28 * V) * n / (ms * 1e-3) / 1e12
             tri["fp64"] = {"achieved_tflops": fl, "peak_tflops": fp64_peak, "frac": fl / fp64_peak,
                            "note": "fp64-pipe bound; peak = in-run DFMA probe"}
+        # end to end through pinned host buffers (a caller's reusable point pool)
+        hxy = ctx.pinned_empty(sc["xy"].shape, np.float32, "g_xy"); hxy[...] = sc["xy"]
+        hX4 = ctx.pinned_empty((4, n), np.float32, "g_X4")
+        hxyz = ctx.pinned_empty((n, 3), np.float64, "g_xyz")
+        ctx.triangulate_batch(sc["P"], hxy, out_X4=hX4, out_xyz=hxyz)
         t0 = time.perf_counter()
-        X4, xyz = ctx.triangulate_batch(sc["P"], sc["xy"])
-        dt = time.perf_counter() - t0
+        for _ in range(3):
+            X4, xyz = ctx.triangulate_batch(sc["P"], hxy, out_X4=hX4, out_xyz=hxyz)
+        dt = (time.perf_counter() - t0) / 3
         tri["e2e"] = {"ms": dt * 1e3, "points_per_s": n / dt, "h2d_bytes": int(sc["xy"].nbytes + sc["P"].nbytes),
                       "d2h_bytes": int(X4.nbytes + xyz.nbytes),
-                      "api": "sfm_triangulate_batch(host xy -> host X4 + xyz), pageable numpy buffers"}
+                      "api": "sfm_triangulate_batch(pinned host xy -> pinned host X4 + xyz)"}
         cam, pt = synth.observations_camera_major(n, V)
         obs = sc["xy"].reshape(-1, 2)
         _, _, ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs, want_cost=False, iters=20)
         b = 32 * n * V + 24 * n
         res = {"ms": ms, "obs_per_s": n * V / (ms * 1e-3),
                "roofline": _roof(b, ms, hbm_gbs, peak_src, bytes_per_obs=32, bytes_per_point=24)}
+        hX = ctx.pinned_empty(sc["X"].shape, np.float64, "g_X"); hX[...] = sc["X"]
+        hcam = ctx.pinned_empty(cam.shape, np.int32, "g_cam"); hcam[...] = cam
+        hpt = ctx.pinned_empty(pt.shape, np.int32, "g_pt"); hpt[...] = pt
+        hobs = ctx.pinned_empty(obs.shape, np.float32, "g_obs"); hobs[...] = obs
+        hres = ctx.pinned_empty((n * V, 2), np.float64, "g_res")
+        ctx.reproject_residuals(sc["intr"], sc["ext"], hX, hcam, hpt, hobs, out_resid=hres)
         t0 = time.perf_counter()
-        r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam, pt, obs)
-        dt = time.perf_counter() - t0
+        for _ in range(3):
+            r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], hX, hcam, hpt, hobs, out_resid=hres)
+        dt = (time.perf_counter() - t0) / 3
         res["e2e"] = {"ms": dt * 1e3, "obs_per_s": n * V / dt,
                       "h2d_bytes": int(sc["X"].nbytes + cam.nbytes + pt.nbytes + obs.nbytes),
-                      "d2h_bytes": int(r.nbytes) + 8, "api": "sfm_reproject_residuals (all tables from the host every call)"}
+                      "d2h_bytes": int(r.nbytes) + 8, "api": "sfm_reproject_residuals (all tables from pinned host memory every call)"}
         # the BA-loop form: tables resident, per evaluation only cameras + points down, cost (8 B) up
         pb = sfm.BAProblem(ctx, V, n, cam, pt, obs)
-        pb.evaluate(sc["intr"], sc["ext"], sc["X"], want_resid=False)
+        pb.evaluate(sc["intr"], sc["ext"], hX, want_resid=False)
         t0 = time.perf_counter()
         for _ in range(5):
-            _, _, c2 = pb.evaluate(sc["intr"], sc["ext"], sc["X"], want_resid=False)
+            _, _, c2 = pb.evaluate(sc["intr"], sc["ext"], hX, want_resid=False)
         dt = (time.perf_counter() - t0) / 5
         res["e2e_ba_loop"] = {"ms": dt * 1e3, "obs_per_s": n * V / dt, "kernel_ms": pb.kernel_ms,
                               "h2d_bytes": int(sc["X"].nbytes + sc["ext"].nbytes), "d2h_bytes": 8,
@@ -649,7 +661,7 @@ def run_pair65536(args, rank, local_rank, world):
     rk = Ranks(rank, local_rank, world)
     n = args.desc if args.desc != 8192 else 65536
     ctx = sfm.Context(local_rank)
-    q, t = synth.sift_like(n, 1000), synth.sift_like(n, 1001)
+    q, t = synth.image_bank(2, n, seed0=1000)             # seeds 1000 / 1001, 20 % shared rows + noise
     lo, hi = shard_query_rows(n, world)[rank]
     hq = ctx.pinned_empty(q.shape, np.float32, "q"); hq[...] = q
     ht = ctx.pinned_empty(t.shape, np.float32, "t"); ht[...] = t
@@ -728,15 +740,26 @@ def run_geometry(args, rank, local_rank, world):
     it = 20
     _, _, tri_ms = ctx.triangulate_batch(sc["P"], xy, want_X4=True, want_xyz=False, iters=it)
     _, _, res_ms = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam_l, pt_l, obs_l, want_cost=False, iters=it)
+    m = e - s
+    hxy = ctx.pinned_empty(xy.shape, np.float32, "g_xy"); hxy[...] = xy
+    hX4 = ctx.pinned_empty((4, m), np.float32, "g_X4")
+    hxyz = ctx.pinned_empty((m, 3), np.float64, "g_xyz")
+    hX = ctx.pinned_empty(sc["X"].shape, np.float64, "g_X"); hX[...] = sc["X"]
+    hcam = ctx.pinned_empty(cam_l.shape, np.int32, "g_cam"); hcam[...] = cam_l
+    hpt = ctx.pinned_empty(pt_l.shape, np.int32, "g_pt"); hpt[...] = pt_l
+    hobs = ctx.pinned_empty(obs_l.shape, np.float32, "g_obs"); hobs[...] = obs_l
+    hres = ctx.pinned_empty((m * V, 2), np.float64, "g_res")
+    ctx.triangulate_batch(sc["P"], hxy, out_X4=hX4, out_xyz=hxyz)
+    ctx.reproject_residuals(sc["intr"], sc["ext"], hX, hcam, hpt, hobs, out_resid=hres)
     rk.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        X4, xyz = ctx.triangulate_batch(sc["P"], xy)
+        X4, xyz = ctx.triangulate_batch(sc["P"], hxy, out_X4=hX4, out_xyz=hxyz)
     tri_e2e = rk.allmax(time.perf_counter() - t0) / args.steps
     rk.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], sc["X"], cam_l, pt_l, obs_l)
+        r, cost = ctx.reproject_residuals(sc["intr"], sc["ext"], hX, hcam, hpt, hobs, out_resid=hres)
     res_e2e = rk.allmax(time.perf_counter() - t0) / args.steps
     tri_ms, res_ms = rk.allmax(tri_ms), rk.allmax(res_ms)
     cost_sum = rk.allsum(cost)
@@ -752,7 +775,7 @@ def run_geometry(args, rank, local_rank, world):
                 "roofline": _roof((8 * V + 16) * (e - s), tri_ms, hbm_gbs, peak_src, bytes_per_point=8 * V + 16, per="rank 0"),
                 "e2e": {"value": n / tri_e2e, "unit": "points/s", "ms_per_step": tri_e2e * 1e3,
                         "h2d_bytes_per_step": int(sc["xy"].nbytes), "d2h_bytes_per_step": int(28 * n),
-                        "api": "sfm_triangulate_batch(host xy -> host X4 + xyz) on every rank's point range"},
+                        "api": "sfm_triangulate_batch(pinned host xy -> pinned host X4 + xyz) on every rank's point range"},
                 "residuals": {"obs_per_s": n * V / (res_ms * 1e-3), "ms": res_ms,
                               "roofline": _roof(32 * (e - s) * V + 24 * n, res_ms, hbm_gbs, peak_src, per="rank 0"),
                               "e2e_obs_per_s": n * V / res_e2e, "e2e_ms": res_e2e * 1e3,

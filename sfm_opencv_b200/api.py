@@ -350,16 +350,20 @@ class Context:
         return total.value, kms.value, tms.value
 
     # ------------------------------------------------------------------ triangulation
-    def triangulate_batch(self, P, xy, want_X4=True, want_xyz=True, iters=0):
-        """P: [V,3,4] float32; xy: [V,N,2] float32. Returns (X4 [4,N] f32, xyz [N,3] f64[, ms])."""
+    def triangulate_batch(self, P, xy, want_X4=True, want_xyz=True, iters=0, out_X4=None, out_xyz=None):
+        """P: [V,3,4] float32; xy: [V,N,2] float32. Returns (X4 [4,N] f32, xyz [N,3] f64[, ms]).
+        out_X4 / out_xyz: caller-owned result arrays (e.g. pinned: pinned_empty) to fill."""
         P = np.ascontiguousarray(P, np.float32).reshape(-1, 3, 4)
         xy = np.ascontiguousarray(xy, np.float32)
         V = P.shape[0]
         if xy.ndim != 3 or xy.shape[0] != V or xy.shape[2] != 2:
             raise SfmError(_capi.SFM_E_INVALID, "xy must be [V,N,2]")
         N = xy.shape[1]
-        X4 = np.empty((4, N), np.float32) if want_X4 else None
-        xyz = np.empty((N, 3), np.float64) if want_xyz else None
+        for o, shp, dt in ((out_X4, (4, N), np.float32), (out_xyz, (N, 3), np.float64)):
+            if o is not None and (o.shape != shp or o.dtype != dt or not o.flags.c_contiguous):
+                raise SfmError(_capi.SFM_E_INVALID, "output array has the wrong shape / dtype")
+        X4 = (out_X4 if out_X4 is not None else np.empty((4, N), np.float32)) if want_X4 else None
+        xyz = (out_xyz if out_xyz is not None else np.empty((N, 3), np.float64)) if want_xyz else None
         pX4 = _ptr(X4, C.c_float) if want_X4 and N else None
         pxyz = _ptr(xyz, C.c_double) if want_xyz and N else None
         if iters > 0:
@@ -374,7 +378,7 @@ class Context:
 
     # ------------------------------------------------------------------ residuals
     def reproject_residuals(self, intr, ext, pts, cam_idx, pt_idx, obs_xy, huber_delta=4.0,
-                            want_resid=True, want_cost=True, iters=0):
+                            want_resid=True, want_cost=True, iters=0, out_resid=None):
         intr = np.ascontiguousarray(intr, np.float64).reshape(4)
         ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 6)
         pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
@@ -382,7 +386,9 @@ class Context:
         pt_idx = np.ascontiguousarray(pt_idx, np.int32)
         obs_xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2)
         n_obs = cam_idx.shape[0]
-        resid = np.empty((n_obs, 2), np.float64) if want_resid else None
+        if out_resid is not None and (out_resid.shape != (n_obs, 2) or out_resid.dtype != np.float64):
+            raise SfmError(_capi.SFM_E_INVALID, "out_resid must be [n_obs,2] float64")
+        resid = (out_resid if out_resid is not None else np.empty((n_obs, 2), np.float64)) if want_resid else None
         cost = C.c_double(0)
         args = [self._h, _ptr(intr, C.c_double), _ptr(ext, C.c_double), ext.shape[0],
                 _ptr(pts, C.c_double), pts.shape[0], _ptr(cam_idx, C.c_int32),

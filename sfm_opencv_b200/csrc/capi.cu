@@ -18,7 +18,7 @@ namespace sfm {
 // match_knn.cu
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
-                        int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream);
+                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, cudaStream_t stream);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 bool knn2_mode_valid(int mode);
 // match_finalize.cu
@@ -60,7 +60,10 @@ cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam,
 cudaError_t launch_residuals(const double intr[4], const double* cam, const double* pts,
                              const int32_t* cam_idx, const int32_t* pt_idx, const float* obs_xy,
                              int64_t n_obs, double huber_delta, double* resid, double* block_cost,
-                             double* cost_out, int grid, cudaStream_t s);
+                             double* cost_out, int grid, cudaStream_t s, const int64_t* seg = nullptr,
+                             int n_cam = 0, int64_t max_seg = 0);
+cudaError_t launch_order_probe(const int32_t* cam_idx, int64_t n_obs, int n_cam, uint32_t* flag,
+                               int64_t* seg, int n_sms, cudaStream_t s);
 }  // namespace sfm
 
 using namespace sfm;
@@ -150,7 +153,7 @@ struct sfm_ctx {
   std::vector<int64_t> kp_off;
   bool kp_ready = false;
   // geometry scratch
-  DevBuf gjtab, gjac, gflag;
+  DevBuf gjtab, gjac, gflag, gseg;
   DevBuf gP, gxy, gX4, gxyz, gext, gcam, gpts, gci, gpi, gobs, gres, gbc, gcost;
 };
 
@@ -264,7 +267,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->pairs,
-                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -626,10 +629,12 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
 // Builds the pair / work-item tables, runs kNN + filter passes, leaves results on the device.
 // q_first / q_count (nullable): pair p matches only query rows [q_first[p], q_first[p] + q_count[p])
 // of its query image (a query-row shard of one huge pair).
+// need_knn: the caller reads the raw kNN rows (knn_raw); otherwise the kNN kernel may stop tracking
+// the second neighbour of rows that cannot pass the ratio test any more (same match lists).
 static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t,
                         const int32_t* q_first, const int32_t* q_count, int n_pairs,
                         double ratio, float dist_floor, float gate_mult, int64_t* total_rows,
-                        bool time_it) {
+                        bool time_it, bool need_knn) {
   if (!ctx) return SFM_E_INVALID;
   if (!ctx->bank_ready)
     return fail(ctx, SFM_E_NOT_UPLOADED,
@@ -747,13 +752,15 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
         CK(cudaStreamWaitEvent(ctx->stream, ctx->img_ev[ctx->h_groups[g].second], 0));
         CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                        ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>() + first,
-                       static_cast<int>(last - first), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+                       static_cast<int>(last - first), ctx->knn.as<Knn2>(), ctx->n_sms,
+                       need_knn ? 0.0 : ratio, ctx->stream));
         ctx->launches += 1;
       }
     } else {
       CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                      ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
-                     static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+                     static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms,
+                     need_knn ? 0.0 : ratio, ctx->stream));
       if (n_items > 0) ctx->launches += 1;
     }
   }
@@ -797,7 +804,8 @@ int sfm_match_pairs(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair_t, 
   if (out_cap < 0 || (out_cap > 0 && !out)) return fail(ctx, SFM_E_INVALID, "bad output buffer");
   int64_t rows = 0;
   ctx->last_valid = false;
-  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, false);
+  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, false,
+                        knn_raw != nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(offsets, ctx->offsets.p, 8 * (n_pairs + 1), cudaMemcpyDeviceToHost,
                      ctx->stream));
@@ -841,7 +849,7 @@ int sfm_match_rows_begin(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pai
   int64_t rows = 0;
   ctx->last_valid = false;
   // dist_floor / gate_mult do not enter pass 1; the counts of this launch are discarded
-  int rc = match_device(ctx, pair_q, pair_t, q_first, q_count, n_pairs, ratio, 0.f, 0.f, &rows, false);
+  int rc = match_device(ctx, pair_q, pair_t, q_first, q_count, n_pairs, ratio, 0.f, 0.f, &rows, false, true);
   if (rc) return rc;
   if (n_pairs)
     CK(cudaMemcpyAsync(min_dist, ctx->min_dist.p, 4 * static_cast<size_t>(n_pairs),
@@ -909,7 +917,7 @@ int sfm_match_pairs_resident(sfm_ctx* ctx, const int32_t* pair_q, const int32_t*
   ctx->last_valid = false;
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, true);
+  int rc = match_device(ctx, pair_q, pair_t, nullptr, nullptr, n_pairs, ratio, dist_floor, gate_mult, &rows, true, false);
   if (rc) return rc;
   int64_t total = 0;
   CK(cudaMemcpyAsync(&total, ctx->offsets.as<int64_t>() + n_pairs, 8, cudaMemcpyDeviceToHost,
@@ -1018,6 +1026,29 @@ static int check_indices(sfm_ctx* ctx, const int32_t* d_cam, const int32_t* d_pt
   CK(cudaMemcpyAsync(&bad, ctx->gflag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad) return fail(ctx, SFM_E_INVALID, "observation refers to a camera or point out of range");
+  return SFM_OK;
+}
+
+// Camera-major probe of an uploaded observation list: *max_seg > 0 and seg filled (device) when
+// cam_idx is sorted and there are at least two cameras with observations; 0 otherwise.
+static int probe_order(sfm_ctx* ctx, const int32_t* d_cam, int64_t n_obs, int n_cam, DevBuf& seg,
+                       int64_t* max_seg) {
+  *max_seg = 0;
+  if (n_cam < 2 || n_cam > 4096 || n_obs < 2) return SFM_OK;
+  CK(ctx->gflag.ensure(4));
+  CK(seg.ensure(8 * (static_cast<size_t>(n_cam) + 1)));
+  CK(launch_order_probe(d_cam, n_obs, n_cam, ctx->gflag.as<uint32_t>(), seg.as<int64_t>(), ctx->n_sms,
+                        ctx->stream));
+  ctx->launches += 2;
+  uint32_t bad = 0;
+  std::vector<int64_t> h(static_cast<size_t>(n_cam) + 1);
+  CK(cudaMemcpyAsync(&bad, ctx->gflag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h.data(), seg.p, 8 * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) return SFM_OK;
+  int64_t m = 0;
+  for (int c = 0; c < n_cam; ++c) m = std::max(m, h[c + 1] - h[c]);
+  *max_seg = m;
   return SFM_OK;
 }
 
@@ -1253,6 +1284,12 @@ static int residual_common(sfm_ctx* ctx, const double intr[4], const double* ext
   }
   CK(launch_camera_table(ctx->gext.as<double>(), n_cam, ctx->gcam.as<double>(), ctx->stream));
   ctx->launches += 1;
+  int64_t max_seg = 0;
+  {
+    const int rc = probe_order(ctx, ctx->gci.as<int32_t>(), n_obs, n_cam, ctx->gseg, &max_seg);
+    if (rc) return rc;
+  }
+  const int64_t* dseg = max_seg > 0 ? ctx->gseg.as<int64_t>() : nullptr;
   double* dres = (resid || iters > 0) ? ctx->gres.as<double>() : nullptr;
   double* dbc = huber_cost ? ctx->gbc.as<double>() : nullptr;
   const int reps = iters > 0 ? iters : 1;
@@ -1260,14 +1297,16 @@ static int residual_common(sfm_ctx* ctx, const double intr[4], const double* ext
   if (iters > 0) {
     CK(launch_residuals(intr, ctx->gcam.as<double>(), ctx->gpts.as<double>(),
                         ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), ctx->gobs.as<float>(),
-                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream));
+                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream,
+                        dseg, n_cam, max_seg));
     ctx->launches += n_launch;
   }
   CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   for (int r = 0; r < reps; ++r) {
     CK(launch_residuals(intr, ctx->gcam.as<double>(), ctx->gpts.as<double>(),
                         ctx->gci.as<int32_t>(), ctx->gpi.as<int32_t>(), ctx->gobs.as<float>(),
-                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream));
+                        n_obs, huber_delta, dres, dbc, ctx->gcost.as<double>(), grid, ctx->stream,
+                        dseg, n_cam, max_seg));
     ctx->launches += n_launch;
   }
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1313,7 +1352,8 @@ struct sfm_ba_problem {
   int n_cam = 0;
   int64_t n_pts = 0, n_obs = 0;
   int grid = 1;
-  DevBuf ci, pi, obs, ext, cam, jtab, pts, res, jac, bc, cost;
+  int64_t max_seg = 0;        // > 0: camera-major list, seg holds the camera segments
+  DevBuf ci, pi, obs, ext, cam, jtab, pts, res, jac, bc, cost, seg;
 };
 
 int sfm_ba_create(sfm_ctx* ctx, int n_cam, int64_t n_pts, const int32_t* cam_idx,
@@ -1355,7 +1395,9 @@ int sfm_ba_create(sfm_ctx* ctx, int n_cam, int64_t n_pts, const int32_t* cam_idx
   CKP(cudaMemcpyAsync(pb->pi.p, pt_idx, 4 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
   CKP(cudaMemcpyAsync(pb->obs.p, obs_xy, 8 * n_obs, cudaMemcpyHostToDevice, ctx->stream));
 #undef CKP
-  const int rc = check_indices(ctx, pb->ci.as<int32_t>(), pb->pi.as<int32_t>(), n_obs, n_cam, n_pts);
+  int rc = check_indices(ctx, pb->ci.as<int32_t>(), pb->pi.as<int32_t>(), n_obs, n_cam, n_pts);
+  if (rc) return drop(rc);
+  rc = probe_order(ctx, pb->ci.as<int32_t>(), n_obs, n_cam, pb->seg, &pb->max_seg);
   if (rc) return drop(rc);
   *out = pb;
   return SFM_OK;
@@ -1368,7 +1410,7 @@ void sfm_ba_destroy(sfm_ctx* ctx, sfm_ba_problem* pb) {
     cudaStreamSynchronize(ctx->stream);
   }
   DevBuf* bufs[] = {&pb->ci, &pb->pi, &pb->obs, &pb->ext, &pb->cam, &pb->jtab, &pb->pts, &pb->res,
-                    &pb->jac, &pb->bc, &pb->cost};
+                    &pb->jac, &pb->bc, &pb->cost, &pb->seg};
   for (DevBuf* b : bufs) b->release();
   delete pb;
 }
@@ -1398,7 +1440,8 @@ int sfm_ba_evaluate(sfm_ctx* ctx, sfm_ba_problem* pb, const double intr[4], cons
     CK(launch_residuals(intr, pb->cam.as<double>(), pb->pts.as<double>(), pb->ci.as<int32_t>(),
                         pb->pi.as<int32_t>(), pb->obs.as<float>(), pb->n_obs, huber_delta,
                         resid ? pb->res.as<double>() : nullptr, huber_cost ? pb->bc.as<double>() : nullptr,
-                        pb->cost.as<double>(), pb->grid, ctx->stream));
+                        pb->cost.as<double>(), pb->grid, ctx->stream,
+                        pb->max_seg > 0 ? pb->seg.as<int64_t>() : nullptr, pb->n_cam, pb->max_seg));
     ctx->launches += huber_cost ? 2 : 1;
   }
   CK(cudaEventRecord(ctx->ev[1], ctx->stream));

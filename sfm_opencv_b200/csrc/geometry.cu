@@ -303,11 +303,25 @@ residual_kernel(double fx, double fy, double cx, double cy, const double* __rest
   // load, two 16-byte residual stores in flight
   const int64_t n2 = n_obs >> 1;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n2;
-       k += stride) {
-    const int2 c = __ldcs(reinterpret_cast<const int2*>(cam_idx) + k);
-    const int2 j = __ldcs(reinterpret_cast<const int2*>(pt_idx) + k);
-    const float4 o = __ldcs(reinterpret_cast<const float4*>(obs_xy) + k);
+  // software pipeline: the loads of the next iteration are issued before the (dependent) point
+  // gathers of this one
+  int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int2 c = make_int2(0, 0), j = make_int2(0, 0);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < n2) {
+    c = __ldcs(reinterpret_cast<const int2*>(cam_idx) + k);
+    j = __ldcs(reinterpret_cast<const int2*>(pt_idx) + k);
+    o = __ldcs(reinterpret_cast<const float4*>(obs_xy) + k);
+  }
+  while (k < n2) {
+    const int64_t kn = k + stride;
+    int2 cn = c, jn = j;
+    float4 on = o;
+    if (kn < n2) {
+      cn = __ldcs(reinterpret_cast<const int2*>(cam_idx) + kn);
+      jn = __ldcs(reinterpret_cast<const int2*>(pt_idx) + kn);
+      on = __ldcs(reinterpret_cast<const float4*>(obs_xy) + kn);
+    }
     const double2 r0 = residual_one(fx, fy, cx, cy, cam, pts, c.x, j.x, make_float2(o.x, o.y));
     const double2 r1 = residual_one(fx, fy, cx, cy, cam, pts, c.y, j.y, make_float2(o.z, o.w));
     if (resid != nullptr) {
@@ -317,6 +331,10 @@ residual_kernel(double fx, double fy, double cx, double cy, const double* __rest
     if (block_cost != nullptr)
       cost += huber_rho(r0.x * r0.x + r0.y * r0.y, huber_delta) +
               huber_rho(r1.x * r1.x + r1.y * r1.y, huber_delta);
+    k = kn;
+    c = cn;
+    j = jn;
+    o = on;
   }
   if ((n_obs & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const int64_t k = n_obs - 1;
@@ -324,6 +342,109 @@ residual_kernel(double fx, double fy, double cx, double cy, const double* __rest
     const double2 r = residual_one(fx, fy, cx, cy, cam, pts, cam_idx[k], pt_idx[k], o);
     if (resid != nullptr) reinterpret_cast<double2*>(resid)[k] = r;
     if (block_cost != nullptr) cost += huber_rho(r.x * r.x + r.y * r.y, huber_delta);
+  }
+  if (block_cost != nullptr) {
+    __shared__ double s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = cost;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += s_part[w];
+      block_cost[blockIdx.x] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera-major observation lists (what bundle_adjustment() builds, NViewReconstuct.cpp:1187-1211)
+// visit the point table once per camera; processed in list order every camera streams the whole
+// table from HBM again (24 B per observation on top of the 32 algorithmic ones: measured 0.58 of
+// the copy rate at 8 views).  When cam_idx is sorted the kernel below walks the list in
+// (chunk of kSegChunk positions) x (camera) order instead, so the cameras read one chunk of
+// points while it is still in L2.  Results are written to the caller's positions: the order of
+// the residual vector does not change.
+constexpr int kSegChunk = 2048;
+
+// flag |= 1 when cam_idx is not non-decreasing
+__global__ void __launch_bounds__(256)
+sorted_check_kernel(const int32_t* __restrict__ cam_idx, int64_t n_obs, uint32_t* __restrict__ flag) {
+  bool bad = false;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k + 1 < n_obs; k += stride)
+    bad |= __ldg(cam_idx + k) > __ldg(cam_idx + k + 1);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+
+// seg[c] = first observation of camera c (lower bound in the sorted cam_idx), seg[n_cam] = n_obs
+__global__ void segment_table_kernel(const int32_t* __restrict__ cam_idx, int64_t n_obs, int n_cam,
+                                     int64_t* __restrict__ seg) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_cam) return;
+  int64_t lo = 0, hi = n_obs;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cam_idx[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  seg[c] = lo;
+}
+
+__global__ void __launch_bounds__(256)
+residual_seg_kernel(double fx, double fy, double cx, double cy, const double* __restrict__ cam,
+                    const double* __restrict__ pts, const int64_t* __restrict__ seg, int n_cam,
+                    int64_t max_seg, const int32_t* __restrict__ pt_idx,
+                    const float* __restrict__ obs_xy, double huber_delta,
+                    double* __restrict__ resid, double* __restrict__ block_cost) {
+  double cost = 0.0;
+  const int n_chunks = static_cast<int>((max_seg + kSegChunk - 1) / kSegChunk);
+  const int n_blocks = n_chunks * n_cam;                          // (chunk, camera) blocks, camera fastest
+  for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const int c = b % n_cam;
+    const int64_t k0 = __ldg(seg + c) + static_cast<int64_t>(b / n_cam) * kSegChunk;
+    const int64_t k1 = min(k0 + kSegChunk, __ldg(seg + c + 1));
+    if (((k0 | k1) & 1) == 0) {
+      // two observations per thread and iteration: 8-byte index loads, one 16-byte observation
+      // load, two 16-byte residual stores in flight
+      // software pipeline: the index / observation loads of the next iteration are issued before
+      // the (dependent) point gathers of this one
+      const int64_t kend = k1 >> 1;
+      int64_t k = (k0 >> 1) + threadIdx.x;
+      int2 j = make_int2(0, 0);
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < kend) {
+        j = __ldcs(reinterpret_cast<const int2*>(pt_idx) + k);
+        o = __ldcs(reinterpret_cast<const float4*>(obs_xy) + k);
+      }
+      while (k < kend) {
+        const int64_t kn = k + 256;
+        int2 jn = j;
+        float4 on = o;
+        if (kn < kend) {
+          jn = __ldcs(reinterpret_cast<const int2*>(pt_idx) + kn);
+          on = __ldcs(reinterpret_cast<const float4*>(obs_xy) + kn);
+        }
+        const double2 r0 = residual_one(fx, fy, cx, cy, cam, pts, c, j.x, make_float2(o.x, o.y));
+        const double2 r1 = residual_one(fx, fy, cx, cy, cam, pts, c, j.y, make_float2(o.z, o.w));
+        if (resid != nullptr) {
+          __stcs(reinterpret_cast<double2*>(resid) + 2 * k, r0);
+          __stcs(reinterpret_cast<double2*>(resid) + 2 * k + 1, r1);
+        }
+        if (block_cost != nullptr)
+          cost += huber_rho(r0.x * r0.x + r0.y * r0.y, huber_delta) +
+                  huber_rho(r1.x * r1.x + r1.y * r1.y, huber_delta);
+        k = kn;
+        j = jn;
+        o = on;
+      }
+    } else {
+      for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) {
+        const float2 o = __ldcs(reinterpret_cast<const float2*>(obs_xy) + k);
+        const double2 r = residual_one(fx, fy, cx, cy, cam, pts, c, __ldcs(pt_idx + k), o);
+        if (resid != nullptr) __stcs(reinterpret_cast<double2*>(resid) + k, r);
+        if (block_cost != nullptr) cost += huber_rho(r.x * r.x + r.y * r.y, huber_delta);
+      }
+    }
   }
   if (block_cost != nullptr) {
     __shared__ double s_part[8];
@@ -704,12 +825,29 @@ cudaError_t launch_jacobians(const double intr[4], const double* ext, int n_cam,
   return cudaGetLastError();
 }
 
+// Camera-major probe: flag (device) != 0 afterwards when cam_idx is not sorted; otherwise seg holds
+// the n_cam + 1 segment offsets.
+cudaError_t launch_order_probe(const int32_t* cam_idx, int64_t n_obs, int n_cam, uint32_t* flag,
+                               int64_t* seg, int n_sms, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(flag, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  if (n_obs > 1) sorted_check_kernel<<<geometry_grid(n_obs, n_sms), 256, 0, s>>>(cam_idx, n_obs, flag);
+  segment_table_kernel<<<(n_cam + 1 + 127) / 128, 128, 0, s>>>(cam_idx, n_obs, n_cam, seg);
+  return cudaGetLastError();
+}
+
+// seg != nullptr (camera-major list, see residual_seg_kernel): max_seg = longest camera segment
 cudaError_t launch_residuals(const double intr[4], const double* cam, const double* pts,
                              const int32_t* cam_idx, const int32_t* pt_idx, const float* obs_xy,
                              int64_t n_obs, double huber_delta, double* resid, double* block_cost,
-                             double* cost_out, int grid, cudaStream_t s) {
-  residual_kernel<<<grid, 256, 0, s>>>(intr[0], intr[1], intr[2], intr[3], cam, pts, cam_idx,
-                                       pt_idx, obs_xy, n_obs, huber_delta, resid, block_cost);
+                             double* cost_out, int grid, cudaStream_t s, const int64_t* seg = nullptr,
+                             int n_cam = 0, int64_t max_seg = 0) {
+  if (seg != nullptr && n_cam > 1)
+    residual_seg_kernel<<<grid, 256, 0, s>>>(intr[0], intr[1], intr[2], intr[3], cam, pts, seg, n_cam,
+                                             max_seg, pt_idx, obs_xy, huber_delta, resid, block_cost);
+  else
+    residual_kernel<<<grid, 256, 0, s>>>(intr[0], intr[1], intr[2], intr[3], cam, pts, cam_idx,
+                                         pt_idx, obs_xy, n_obs, huber_delta, resid, block_cost);
   if (block_cost != nullptr) cost_sum_kernel<<<1, 256, 0, s>>>(block_cost, grid, cost_out);
   return cudaGetLastError();
 }

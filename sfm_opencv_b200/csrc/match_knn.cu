@@ -66,20 +66,34 @@ constexpr int kAccBufs = 2;                     // TMEM accumulator buffers (2 x
 constexpr int kFirstMmaWarp = 4;                // warps 1..3 idle (warpgroup granularity)
 constexpr int kMmaWarps = 4;                    // (query half, tile parity)
 constexpr int kFirstEpiWarp = kFirstMmaWarp + kMmaWarps;
-constexpr int kEpiWarps = 16;                   // 2 halves x 2 column halves x 4 lane quarters
-constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;       // 768
+// The 128 columns of a tile are split over kParts epilogue threads per query row:
+//   2 parts: 64 + 64 columns, 16 epilogue warps (4 per SM sub-partition), 104 registers each
+//   3 parts: 48 + 48 + 32 columns, 24 epilogue warps (6 per sub-partition, the CTA is 1024 threads),
+//            72 registers each -- more runnable warps to overlap the latency-bound hit path of
+//            one warp with the ALU-bound max trees of the others
+#ifndef SFM_EPI_PARTS
+#define SFM_EPI_PARTS 2
+#endif
+constexpr int kParts = SFM_EPI_PARTS;
+static_assert(kParts == 2 || kParts == 3, "column parts per query row");
+constexpr int kEpiWarps = 8 * kParts;           // 2 halves x kParts column parts x 4 lane quarters
+constexpr int kKnnThreads = (kFirstEpiWarp + kEpiWarps) * 32;       // 768 / 1024
+constexpr int kRegsLaunch = kParts == 2 ? 80 : 64;                  // 65536 / threads, multiple of 8
 constexpr int kRegsProd = 24;                   // setmaxnreg: producer warpgroup (warps 0..3)
 constexpr int kRegsMma = 40;                    // setmaxnreg: MMA warpgroup (warps 4..7)
-constexpr int kRegsEpi = 104;                   // setmaxnreg: epilogue warpgroups
-static_assert(4 * kRegsProd + 4 * kRegsMma + 16 * kRegsEpi <= 24 * 80,
-              "register pool of the CTA (768 x 80)");
+constexpr int kRegsEpi = kParts == 2 ? 104 : 72;                    // setmaxnreg: epilogue warpgroups
+static_assert(4 * kRegsProd + 4 * kRegsMma + kEpiWarps * kRegsEpi <= (kFirstEpiWarp + kEpiWarps) * kRegsLaunch,
+              "register pool of the CTA");
+// part p owns columns [part_col0(p), part_col0(p) + 32 + 8 * part_bgroups(p)): a 32-column piece A
+// (four 8-column groups) and a piece B of part_bgroups(p) groups
+__host__ __device__ constexpr int part_col0(int p) { return kParts == 2 ? 64 * p : 48 * p; }
+__host__ __device__ constexpr int part_bgroups(int p) { return kParts == 2 ? 4 : (p < 2 ? 2 : 0); }
 constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-key window (8)
 #ifndef SFM_COLD_WINDOWS
 #define SFM_COLD_WINDOWS 1                      // windows at the start of a sweep that skip the filter
 #endif
 constexpr int kPreVoteTiles = 128;              // sweeps of >= 16384 train rows use the chunk pre-vote
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
-constexpr int kColsPerThread = kTileN / 2;      // 64 columns of each tile per epilogue thread
 constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
 
 constexpr uint32_t kABytes = kTileM * kDim;     // 32 KB
@@ -104,8 +118,8 @@ constexpr uint32_t kOffB = kOffA + 2 * kABytes;
 constexpr uint32_t kOffCk = kOffB + kStages * kBBytes;
 constexpr uint32_t kOffGm = kOffCk + kCkSlots * kCkBytes;
 constexpr uint32_t kOffInfo = kOffGm + kCkSlots * kGmBytes;
-constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x 256 rows x int4
-constexpr uint32_t kOffShare = kOffMerge + 2 * kTileM * 16;            // 256 rows x 2 x int4
+constexpr uint32_t kOffMerge = kOffInfo + 2 * sizeof(ItemInfo);        // 2 x (kParts - 1) x 256 rows x int4
+constexpr uint32_t kOffShare = kOffMerge + 2 * (kParts - 1) * kTileM * 16;   // 256 rows x 32 B (8 per part)
 constexpr uint32_t kOffBar = kOffShare + kTileM * 32;
 constexpr uint32_t kNumBars = 2 * kStages + 4 + 4 * kAccBufs;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
@@ -195,48 +209,62 @@ __device__ __forceinline__ int group_max(const uint32_t* r) {
   return max(__vimax3_s32(a, b, r[6]), static_cast<int>(r[7]));
 }
 
-// Top-2 update with one 32-column chunk (4 groups) of a tile; ck_addr / gm_addr = shared
-// addresses of the chunk's column keys and shifted group minima.
+// Top-2 update with one piece of a tile: kG groups of 8 columns (4 for a 32-column piece);
+// ck_addr / gm_addr = shared addresses of the piece's column keys and group minima.
 //   kMode 0: every group is inserted (2.5 min/max + 1 IMAD per element).
 //   kMode 1: only groups whose smallest possible value beats the bound of some row of the
 //            warp: per group one IMAD, one compare and one vote on top of the max tree.
 //            neg2 = -2 in a register ptxas cannot see through, so that the multiply-add stays
 //            an IMAD on the FMA pipe instead of an IADD3 on the (limiting) ALU pipe.
-//   kPreVote : one vote for the whole chunk in front of the four per-group votes.  A vote costs
-//            about two ALU instructions; in long sweeps (rare hits) most chunks need only that
-//            one, in 8192-column sweeps 54 % of the chunks contain a hit and it does not pay
-//            (measured: -2.6 % there, +7 % on a 65536-column train image), so the kernel picks
-//            per work item.
+//   kPreVote : one vote for the whole piece in front of the per-group votes.  A vote costs
+//            about two ALU instructions; in long sweeps (rare hits) most pieces need only that
+//            one, in 8192-column sweeps 54 % of the 32-column pieces contain a hit and it does
+//            not pay (measured: -2.6 % there, +7 % on a 65536-column train image), so the kernel
+//            picks per work item.
 // `mid` runs once inside the update, after the filter votes and before the inserts (the sweep
 // hands the TMEM buffer back there).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
-template <int kMode, bool kPreVote, class Mid = NoHook>
-__device__ __forceinline__ void chunk_update(const uint32_t (&r)[32], uint32_t ck_addr,
+template <int kMode, bool kPreVote, int kG, class Mid = NoHook>
+__device__ __forceinline__ void chunk_update(const uint32_t (&r)[8 * kG], uint32_t ck_addr,
                                              uint32_t gm_addr, int neg2, RowTop2& s, Mid mid = Mid()) {
+  static_assert(kG == 2 || kG == 4, "piece of 16 or 32 columns");
   if constexpr (kMode == 0) {
     group_insert(&r[0], ck_addr, s);
     mid();
 #pragma unroll
-    for (int j = 1; j < 4; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
+    for (int j = 1; j < kG; ++j) group_insert(&r[8 * j], ck_addr + 32 * j, s);
   } else {
-    const int4 nn = lds_v4(gm_addr);
-    const int n8[4] = {nn.x, nn.y, nn.z, nn.w};
-    bool h[4];
+    int n8[kG];
+    if constexpr (kG == 4 && kParts == 2) {
+      const int4 nn = lds_v4(gm_addr);
+      n8[0] = nn.x; n8[1] = nn.y; n8[2] = nn.z; n8[3] = nn.w;
+    } else {                              // 3 parts: a piece starts at a multiple of 8 bytes only
+#pragma unroll
+      for (int j = 0; j < kG; j += 2) {
+        const int2 nn = lds_v2(gm_addr + 4 * j);
+        n8[j] = nn.x; n8[j + 1] = nn.y;
+      }
+    }
+    bool h[kG];
     if constexpr (kPreVote) {
-      bool p[4];
+      bool p[kG];
+      bool any = false;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
-      if (!__any_sync(0xffffffffu, p[0] | p[1] | p[2] | p[3])) { mid(); return; }
+      for (int j = 0; j < kG; ++j) {
+        p[j] = group_max(&r[8 * j]) * neg2 + n8[j] < s.bv;
+        any |= p[j];
+      }
+      if (!__any_sync(0xffffffffu, any)) { mid(); return; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __any_sync(0xffffffffu, p[j]);
+      for (int j = 0; j < kG; ++j) h[j] = __any_sync(0xffffffffu, p[j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < kG; ++j)
         h[j] = __any_sync(0xffffffffu, group_max(&r[8 * j]) * neg2 + n8[j] < s.bv);
     }
     mid();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kG; ++j) {
       if (h[j]) {
         group_insert(&r[8 * j], ck_addr + 32 * j, s);
         s.bv = min(s.bv, s.m2 >> kColBits);
@@ -255,11 +283,21 @@ __device__ __forceinline__ void close_window(RowTop2& s, int base) {
   s.m2 = INT32_MAX;
 }
 
-template <int kMode>
+// kMatchOnly (mode 1 only): the caller wants match lists, not the raw kNN rows.  A row whose
+// current top-2 fails Lowe's ratio test for sure (d0^2 > ratio2 * d1^2, ratio2 = ratio^2 with a
+// margin that covers the float sqrt and the double compare of the real test) can only become a
+// match through a NEW BEST neighbour; a column between its best and second best can only make the
+// test fail harder.  Such rows bound with their best value instead of their second best (decided
+// once per packed-key window, no cost per hit).  If a new best does arrive the pair (new best, old
+// best) is the exact top-2 again -- every skipped column was no better than the old best -- so
+// rows that pass, their distances and min_dist are exactly those of the full search; for rows
+// that fail, Knn2::j1 / d1 may name a column that is not the true second neighbour (it is never
+// better than the true one, so the row fails the real test too).
+template <int kMode, bool kMatchOnly = false>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ ckey,
             const int32_t* __restrict__ gmin8, const int32_t* __restrict__ norm, const PairDesc* __restrict__ pairs,
-            const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg) {
+            const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg, float ratio2) {
   extern __shared__ uint8_t smem_raw[];
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -305,8 +343,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     fence_mbar_init();
   }
   if (threadIdx.x < kTileM)    // tagged (best, second best) slots of the row-sharing threads
-    for (int h = 0; h < 2; ++h)
-      sts_v2(smem_base + kOffShare + threadIdx.x * 32 + h * 16, 0xffffffffu, 0xffffffffu);
+    for (int h = 0; h < kParts; ++h)
+      sts_v2(smem_base + kOffShare + threadIdx.x * 32 + h * 8, 0xffffffffu, 0xffffffffu);
   if (warp == kFirstMmaWarp) {
     tmem_alloc(smem_base + kOffTmemPtr, 512);
     tmem_relinquish();
@@ -424,17 +462,17 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     // ===================================================== epilogue: running top-2 per row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     const int e = warp - kFirstEpiWarp;            // 4 consecutive warps cover the 4 quarters
-    const int half = e >> 3;                       // which 128-row half of the block
-    const int chalf = (e >> 2) & 1;                // which 64-column half of every tile
+    const int half = (e >> 2) / kParts;            // which 128-row half of the block
+    const int part = (e >> 2) % kParts;            // which column part of every tile
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int row_in_blk = half * kHalfM + quarter * 32 + lane;
+    const int col0 = kParts == 2 ? 64 * part : 48 * part;           // == part_col0(part)
     // Loop invariants that ptxas would otherwise re-derive from %tid in front of every use
     // (8 ALU instructions each time): pin them in registers.
-    uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * kTileN +
-                      chalf * kColsPerThread;
+    uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * kTileN + col0;
     uint32_t bar_tf = bar_t_full(0, half), bar_te = bar_t_empty(0, half);   // + 16 * buffer
-    uint32_t ck_base = sCk + chalf * (kColsPerThread * 4);
-    uint32_t gm_base = sGm + chalf * (kColsPerThread / 8 * 4);
+    uint32_t ck_base = sCk + col0 * 4;
+    uint32_t gm_base = sGm + col0 / 8 * 4;
     int neg2 = -2;
     asm volatile("" : "+r"(t_addr), "+r"(bar_tf), "+r"(bar_te), "+r"(ck_base), "+r"(gm_base),
                  "+r"(neg2));
@@ -445,18 +483,18 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     bar_te = __shfl_sync(0xffffffffu, bar_te, 0);
     ck_base = __shfl_sync(0xffffffffu, ck_base, 0);
     gm_base = __shfl_sync(0xffffffffu, gm_base, 0);
-    const uint32_t merge_addr = smem_base + kOffMerge + row_in_blk * 16;
-    const uint32_t share_own = smem_base + kOffShare + row_in_blk * 32 + chalf * 16;
-    const uint32_t share_other = smem_base + kOffShare + row_in_blk * 32 + (chalf ^ 1) * 16;
-    const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the two column halves
+    const uint32_t merge_row = smem_base + kOffMerge + row_in_blk * 16;
+    const uint32_t share_row = smem_base + kOffShare + row_in_blk * 32;
+    const int pair_bar = 1 + half * 4 + quarter;   // named barrier of the kParts warps of a row set
     uint32_t buf = 0, bphase = 0, abuf = 0, mslot = 0, tile_seq = 0, item_seq = 0;
     for (int item = blockIdx.x; item < n_items && !SFM_DBG(2); item += gridDim.x) {
       RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
       int ntiles = 1, rows_valid = 0, norm_row = 0;
       int64_t knn_row = 0;
       if constexpr (kMode <= 1) {
-        // ---- sweep: a tile is two 32-column chunks per thread; the tcgen05.ld of chunk 1 is
-        // in flight while chunk 0 is processed, and the buffer is released between the two
+        // ---- sweep: a thread's share of a tile is a 32-column piece A and (except for the last
+        // of three parts) a piece B; the tcgen05.ld of piece B is in flight while piece A is
+        // processed, and the buffer is released between the two
         mbar_wait(bar_tf + 16 * buf, bphase);
         tc_fence_after();
         ntiles = info[abuf].ntiles;
@@ -467,20 +505,26 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_empty(abuf));
         abuf ^= 1;
-        uint32_t ra[32], rb[32];
+        // |q|^2 of this thread's row (padding rows of the bank carry a sentinel: any value works)
+        [[maybe_unused]] int nq2 = 0;
+        if constexpr (kMatchOnly) nq2 = row_in_blk < rows_valid ? __ldg(norm + norm_row + row_in_blk) : 0;
+        uint32_t ra[32];
         tmem_ld_x32(t_addr + buf * (2 * kTileN), ra);
         tmem_ld_wait();
-        // the sweep in two compiled flavours (with / without the chunk-level pre-vote, see
-        // chunk_update); long train images take the pre-vote one
-        auto sweep = [&](auto mode_tag, auto pre_tag, int w_first, int w_last) {
+        // the sweep in compiled flavours (insert-all / filtered, with / without the piece-level
+        // pre-vote, groups of piece B); long train images take the pre-vote one
+        auto sweep = [&](auto mode_tag, auto pre_tag, auto bg_tag, int w_first, int w_last) {
           constexpr int kM = decltype(mode_tag)::value;      // 0: insert every group, 1: filtered
           constexpr bool kPre = decltype(pre_tag)::value;
+          constexpr int kBG = decltype(bg_tag)::value;       // groups of piece B: 4, 2 or 0
+        uint32_t rb[kBG > 0 ? 8 * kBG : 8];
         // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
         // behind the inner loop, not behind a per-tile test
         for (int w0 = w_first; w0 < w_last; w0 += kWinTiles) {
         const int wend = min(w0 + kWinTiles, ntiles);
         for (int t = w0; t < wend; ++t) {
-          tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);    // chunk 1 in flight
+          if constexpr (kBG == 4) tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);   // piece B in flight
+          if constexpr (kBG == 2) tmem_ld_x16(t_addr + buf * (2 * kTileN) + 32, rb);
           const uint32_t slot = tile_seq % kCkSlots;
           const uint32_t ck_addr = ck_base + slot * kCkBytes;
           const uint32_t gm_addr = gm_base + slot * kGmBytes;
@@ -490,24 +534,27 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             __syncwarp();
             mbar_arrive_elected(bar_te + 16 * buf);
           };
-          if constexpr (kPre) {
-            chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st);
+          if constexpr (kBG == 0) {
+            release();                                          // piece A is the whole share
+            chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st);
+          } else if constexpr (kPre) {
+            chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st);
             release();
           } else {
-            // released from inside chunk 0 (after its votes, before its inserts): chunk 1 has
+            // released from inside piece A (after its votes, before its inserts): piece B has
             // landed by then, and the MMA of tile t+2 starts a third of a tile earlier (+0.9 %)
-            chunk_update<kM, kPre>(ra, ck_addr, gm_addr, neg2, st, release);
+            chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st, release);
           }
           const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
-          chunk_update<kM, kPre>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
-          // Tile t+1 is asked for only now, not before chunk 1: the 8 warps that share a TMEM
+          if constexpr (kBG > 0) chunk_update<kM, kPre, kBG>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+          // Tile t+1 is asked for only now, not before piece B: the warps that share a TMEM
           // buffer drift apart by their hit counts, and the MMA of tile t+1 starts when the
           // slowest of them released tile t-1 -- waiting half a tile later keeps 44 % of the
           // waits from sleeping (measured: +5 %, more than the exposed tcgen05.ld costs)
           if (t + 1 < ntiles) {
             mbar_wait(bar_tf + 16 * nbuf, nphase);
             tc_fence_after();
-            tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // chunk 0 of tile t+1
+            tmem_ld_x32(t_addr + nbuf * (2 * kTileN), ra);      // piece A of tile t+1
             tmem_ld_wait();
           }
           ++tile_seq;
@@ -516,24 +563,34 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         }
           {
             // close the 1024-column window, then tighten the bound, also with the row
-            // partner's top-2 (ties with the partner's columns go by index: + 1)
+            // partners' top-2 (ties with the partners' columns go by index: + 1)
             close_window(st, w0 * kTileN);
             int bound = st.g2v;
             if (kMode == 1) {
-              // the row's second best over BOTH column halves bounds what can still enter:
-              // second smallest of {own best, own second, partner's best, partner's second}
+              // the row's second best over ALL column parts bounds what can still enter: second
+              // smallest of the union of the parts' (best, second).
               // Each 32-bit word carries its own tag (this CTA's item counter, 10 bits), so the
               // exchange needs neither a barrier nor an atomic 8-byte access: a word of an older
               // item, or a pair torn between two items, fails the tag test and is ignored (the
-              // partner is never more than one item away: bar.sync at every item end).  Values
+              // partners are never more than one item away: bar.sync at every item end).  Values
               // are < 2^21 in magnitude (a missing second best is clamped to 2^21 - 1).
               constexpr int kNone = (1 << 21) - 1;
               const int tag = static_cast<int>(item_seq & 1023u);
-              sts_v2(share_own, min(st.g1v, kNone) * 1024 + tag, min(st.g2v, kNone) * 1024 + tag);
-              const int2 o = lds_v2(share_other);   // any earlier value of this item is valid
-              if (((o.x & 1023) == tag) & ((o.y & 1023) == tag)) {
-                const int joint = min(max(st.g1v, o.x >> 10), o.y >> 10);
-                if (joint < kNone) bound = min(bound, joint + 1);
+              sts_v2(share_row + part * 8, min(st.g1v, kNone) * 1024 + tag, min(st.g2v, kNone) * 1024 + tag);
+              int j1 = min(st.g1v, kNone), j2 = min(st.g2v, kNone);
+#pragma unroll
+              for (int o = 1; o < kParts; ++o) {
+                const int op = part + o >= kParts ? part + o - kParts : part + o;
+                const int2 w = lds_v2(share_row + op * 8);   // any earlier value of this item is valid
+                if (((w.x & 1023) == tag) & ((w.y & 1023) == tag)) merge_top2(j1, j2, w.x >> 10, w.y >> 10);
+              }
+              if (j2 < kNone) {
+                bound = min(bound, j2 + 1);
+                if constexpr (kMatchOnly) {
+                  // squared distances are exact integers < 2^22: exact in float
+                  const float d0 = static_cast<float>(j1 + nq2), d1 = static_cast<float>(j2 + nq2);
+                  if (d0 > ratio2 * d1) bound = min(bound, j1);
+                }
               }
             }
             st.bv = bound;
@@ -545,9 +602,17 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         // compare, vote, branch) costs more than it saves.
         constexpr int kCold = kMode == 1 ? SFM_COLD_WINDOWS * kWinTiles : 0;
         const int cold = min(kCold, ntiles);
-        if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, 0, cold);
-        if (ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, cold, ntiles);
-        else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, cold, ntiles);
+        auto sweeps = [&](auto bg_tag) {
+          if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, bg_tag, 0, cold);
+          if (ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, bg_tag, cold, ntiles);
+          else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, bg_tag, cold, ntiles);
+        };
+        if constexpr (kParts == 2) {
+          sweeps(std::integral_constant<int, 4>{});
+        } else {
+          if (part < 2) sweeps(std::integral_constant<int, 2>{});
+          else sweeps(std::integral_constant<int, 0>{});
+        }
       } else {
 #ifdef SFM_EXPERIMENTS
         // ---- timing experiments only (results are garbage):
@@ -592,15 +657,18 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
 #endif
       }
       ++item_seq;
-      // merge the two column halves of the row: the upper half hands its top-2 over
-      const uint32_t slot = merge_addr + mslot * (kTileM * 16);
+      // merge the column parts of the row: parts 1.. hand their top-2 over to part 0
+      const uint32_t slot = merge_row + mslot * ((kParts - 1) * kTileM * 16);
       mslot ^= 1;
-      if (chalf == 1) sts_v4(slot, st.g1v, st.g1i, st.g2v, st.g2i);
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      if (chalf == 0) {
-        const int4 o = lds_v4(slot);
-        insert_vi(st, o.x, o.y);
-        insert_vi(st, o.z, o.w);
+      if (part > 0) sts_v4(slot + (part - 1) * (kTileM * 16), st.g1v, st.g1i, st.g2v, st.g2i);
+      asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
+      if (part == 0) {
+#pragma unroll
+        for (int o = 0; o < kParts - 1; ++o) {
+          const int4 w = lds_v4(slot + o * (kTileM * 16));
+          insert_vi(st, w.x, w.y);
+          insert_vi(st, w.z, w.w);
+        }
         if (row_in_blk < rows_valid) {
           const int nq2 = __ldg(norm + norm_row + row_in_blk);
           Knn2 out;
@@ -709,15 +777,16 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int variant)
 // The shared-memory opt-in is a per-device attribute of the kernel: it is set on every launch
 // (a host-side table lookup), so contexts on several devices -- one per host thread, as
 // INTEGRATION.md recommends -- each get it.
-template <int kMode>
+template <int kMode, bool kMatchOnly>
 static cudaError_t launch_knn2_mode(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* gmin8,
                                     const int32_t* norm, const PairDesc* pairs, const int2* items,
-                                    int n_items, Knn2* knn_out, int grid, int dbg, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(knn2_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kKnnSmemBytes);
+                                    int n_items, Knn2* knn_out, int grid, int dbg, float ratio2,
+                                    cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(knn2_kernel<kMode, kMatchOnly>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes);
   if (e != cudaSuccess) return e;
-  knn2_kernel<kMode><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(tmap, ckey, gmin8, norm, pairs, items,
-                                                                   n_items, knn_out, dbg);
+  knn2_kernel<kMode, kMatchOnly><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(
+      tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, dbg, ratio2);
   return cudaGetLastError();
 }
 
@@ -729,23 +798,30 @@ bool knn2_mode_valid(int mode) {
 #endif
 }
 
+// match_ratio > 0: the caller needs match lists only (see kMatchOnly); 0: exact kNN rows.
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
-                        int n_items, Knn2* knn_out, int n_sms, cudaStream_t stream) {
+                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, cudaStream_t stream) {
   if (!knn2_mode_valid(mode)) return cudaErrorInvalidValue;
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
 #ifdef SFM_EXPERIMENTS
   const int dbg = mode >> 4;   // timing experiments (results invalid), see tools/exp_modes.py
   mode &= 15;
-  if (mode == 4) return launch_knn2_mode<4>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
-  if (mode == 3) return launch_knn2_mode<3>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
-  if (mode == 2) return launch_knn2_mode<2>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+  if (mode == 4) return launch_knn2_mode<4, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
+  if (mode == 3) return launch_knn2_mode<3, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
+  if (mode == 2) return launch_knn2_mode<2, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
 #else
   const int dbg = 0;
 #endif
-  if (mode == 0) return launch_knn2_mode<0>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
-  return launch_knn2_mode<1>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, stream);
+  if (mode == 0) return launch_knn2_mode<0, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
+  if (match_ratio > 0.0 && match_ratio <= 1.0) {
+    // the real test is (double)sqrtf(d0) > ratio * (double)sqrtf(d1): two float roundings of
+    // 6e-8 each, squared; a relative margin of 1e-5 on ratio^2 keeps "fails for sure" sure
+    const float ratio2 = static_cast<float>(match_ratio * match_ratio * (1.0 + 1e-5));
+    return launch_knn2_mode<1, true>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, ratio2, stream);
+  }
+  return launch_knn2_mode<1, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
 }
 
 // iters > 0: 128x256x32 MMAs; iters < 0: -(n << 4 | variant): the same work as 128x128x32

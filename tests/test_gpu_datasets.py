@@ -19,6 +19,10 @@ def _knn_arrays(k):
     return dist, idx
 
 
+def _same_lists(a, b):
+    return a.flat.tobytes() == b.flat.tobytes() and np.array_equal(a.offsets, b.offsets)
+
+
 def test_dog_consecutive_pairs(ctx, golden):
     """dataset/dog: 16 images of 4.6k-21.8k SIFT descriptors, 15 consecutive pairs
     (match_features_for_all, NViewReconstuct.cpp:857-870): every kNN row (digest) and every match
@@ -33,6 +37,10 @@ def test_dog_consecutive_pairs(ctx, golden):
         assert np.array_equal(m[i]["trainIdx"], g[f"match_{i}"][:, 1])
         assert np.array_equal(_bits(m[i]["distance"]), _bits(g[f"match_dist_{i}"]))
         assert _bits(md[i]) == _bits(g[f"min_dist_{i}"])
+    # match lists only (no raw kNN rows requested): the kernel stops tracking the second
+    # neighbour of rows that cannot pass the ratio test any more -- same lists, same min_dist
+    m2, md2, _ = ctx.match_pairs(M.consecutive_pairs(n))
+    assert _same_lists(m, m2) and md.tobytes() == md2.tobytes()
 
 
 @pytest.mark.parametrize("name", ["crazyhorse", "desktop"])
@@ -52,6 +60,10 @@ def test_real_datasets_all_pairs(ctx, golden, name):
         assert np.array_equal(m[p]["trainIdx"], ap[f"match_{p}"][:, 1])
         assert np.array_equal(_bits(m[p]["distance"]), _bits(ap[f"match_dist_{p}"]))
         assert _bits(md[p]) == _bits(ap[f"min_dist_{p}"])
+    for ratio in (0.6, 0.8, 0.95, 1.0, 0.3):
+        a, amd, _ = ctx.match_pairs(pairs, ratio=ratio, want_knn=True)     # exact kNN rows
+        b, bmd, _ = ctx.match_pairs(pairs, ratio=ratio)                    # match lists only
+        assert _same_lists(a, b) and amd.tobytes() == bmd.tobytes(), ratio
 
 
 # ---- property tests -------------------------------------------------------------------------
@@ -73,6 +85,8 @@ def test_property_kernel_equals_oracle(ctx, qt):
     om, od, omd = M.filter_matches(d, idx)
     assert np.array_equal(m[0]["queryIdx"], om[:, 0]) and np.array_equal(m[0]["trainIdx"], om[:, 1])
     assert np.array_equal(_bits(m[0]["distance"]), _bits(od)) and _bits(md[0]) == _bits(omd)
+    m2, md2, _ = ctx.match_pairs([(0, 1)])                   # match lists only
+    assert _same_lists(m, m2) and md.tobytes() == md2.tobytes()
 
 
 @settings(max_examples=20, deadline=None,
@@ -86,6 +100,28 @@ def test_property_long_train_sets(ctx, qt):
     d, idx = M.knn2_int(q, t)
     dist, gi = _knn_arrays(knn[0])
     assert np.array_equal(gi, idx) and np.array_equal(_bits(dist), _bits(d))
+    for ratio in (0.6, 0.9):
+        a, amd, _ = ctx.match_pairs([(0, 1)], ratio=ratio, want_knn=True)
+        b, bmd, _ = ctx.match_pairs([(0, 1)], ratio=ratio)
+        assert _same_lists(a, b) and amd.tobytes() == bmd.tobytes()
+
+
+def test_match_only_mode_on_the_headline_shape(ctx):
+    """8192-row images with planted near-duplicates (BASELINE config 3's generator): the lists of
+    the match-only sweep equal those of the exact sweep for every pair and several ratios."""
+    from oracle import synth
+    bank = synth.image_bank(5, 8192, seed0=31)
+    ctx.upload_descriptors(bank)
+    pairs = M.all_pairs(5)
+    for ratio in (0.6, 0.75, 0.99):
+        a, amd, _ = ctx.match_pairs(pairs, ratio=ratio, want_knn=True)
+        b, bmd, _ = ctx.match_pairs(pairs, ratio=ratio)
+        assert _same_lists(a, b) and amd.tobytes() == bmd.tobytes(), ratio
+        assert len(a.flat) > 1000
+    om, od, omd, _, _ = M.match_features(bank[0], bank[1], knn=M.knn2_cv)
+    b, bmd, _ = ctx.match_pairs([(0, 1)])
+    assert np.array_equal(b[0]["queryIdx"], om[:, 0]) and np.array_equal(b[0]["trainIdx"], om[:, 1])
+    assert np.array_equal(_bits(b[0]["distance"]), _bits(od)) and _bits(bmd[0]) == _bits(omd)
 
 
 def test_max_norm_rows_and_rejected_rows(ctx):
