@@ -19,7 +19,14 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[h], [r for r in rows[h + 1:] if len(r) == len(rows[h])]
+# a report may hold several launches (one source page each): take the first one
+data = []
+for r in rows[h + 1:]:
+    if r and r[0] == "Address":
+        break
+    if len(r) == len(rows[h]):
+        data.append(r)
+hdr = rows[h]
 col = {name: hdr.index(name) for name in hdr}
 ex = [int(r[col["Instructions Executed"]]) for r in data]
 smp = [int(r[col["# Samples"]]) for r in data]
