@@ -17,7 +17,8 @@ NVCC_FLAGS = [
 # The CUDA runtime is linked as a shared library (libcudart.so.12 of the image, or the copy a host
 # process such as torch has already loaded): the library then carries none of the runtime's own
 # symbol table, and shares streams / the primary context with its host process.
-LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+LINK_FLAGS = ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def _nvcc() -> str:

@@ -58,6 +58,24 @@ namespace sfm {
 #define SFM_DBG(bit) false
 #endif
 
+// -DSFM_CHECKS: protocol / bounds assertions in the kernel (compute-sanitizer is closed on the GPU
+// pool this was developed on, profiles/r2_sanitizer_unavailable.txt): work-item tables, TMEM and
+// shared-memory ring addresses, result rows and the tag discipline of the bound exchange are checked
+// on the device and trap with a message.  The GPU tests are run once against this build
+// (tools/variants.py build chk:-DSFM_CHECKS; profiles/r2_checks_build_tests.txt).
+#ifdef SFM_CHECKS
+#define SFM_ASSERT(cond, what)                                                                  \
+  do {                                                                                          \
+    if (!(cond)) {                                                                              \
+      printf("sfm_b200 check failed: %s (block %d thread %d, %s:%d)\n", what, blockIdx.x,      \
+             threadIdx.x, __FILE__, __LINE__);                                                  \
+      __trap();                                                                                 \
+    }                                                                                           \
+  } while (0)
+#else
+#define SFM_ASSERT(cond, what) do { } while (0)
+#endif
+
 #ifndef SFM_STAGES
 #define SFM_STAGES 6                            // tools/variants.py builds other depths with -D
 #endif
@@ -372,6 +390,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         const int mblk = it.y;
         const int ntiles = (pd.nt + kTileN - 1) / kTileN;
         const int t_row0 = pd.t_row0;
+        SFM_ASSERT(pd.nt >= 2 && pd.nq > 0 && mblk >= 0 && mblk * kTileM < pd.nq, "work item outside its pair");
+        SFM_ASSERT(pd.q_row0 >= 0 && pd.t_row0 >= 0 && pd.knn_off >= 0, "negative bank / result row");
         mbar_wait(bar_a_empty(abuf), aphase ^ 1);
         if (elect_one()) {
           info[abuf].ntiles = ntiles;
@@ -505,6 +525,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_empty(abuf));
         abuf ^= 1;
+        SFM_ASSERT(ntiles >= 1 && rows_valid >= 1 && knn_row >= 0, "item info not published");
+        SFM_ASSERT(buf < kAccBufs && (tile_seq % kCkSlots) < kCkSlots, "accumulator / key ring index");
         // |q|^2 of this thread's row (padding rows of the bank carry a sentinel: any value works)
         [[maybe_unused]] int nq2 = 0;
         if constexpr (kMatchOnly) nq2 = row_in_blk < rows_valid ? __ldg(norm + norm_row + row_in_blk) : 0;
@@ -582,6 +604,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
               for (int o = 1; o < kParts; ++o) {
                 const int op = part + o >= kParts ? part + o - kParts : part + o;
                 const int2 w = lds_v2(share_row + op * 8);   // any earlier value of this item is valid
+                SFM_ASSERT((w.x & 1023) == (w.y & 1023) || ((((w.x & 1023) - (w.y & 1023)) & 1023) == 1) ||
+                               ((((w.y & 1023) - (w.x & 1023)) & 1023) == 1),
+                           "bound exchange: words more than one item apart");
                 if (((w.x & 1023) == tag) & ((w.y & 1023) == tag)) merge_top2(j1, j2, w.x >> 10, w.y >> 10);
               }
               if (j2 < kNone) {
@@ -671,6 +696,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         }
         if (row_in_blk < rows_valid) {
           const int nq2 = __ldg(norm + norm_row + row_in_blk);
+          SFM_ASSERT(st.g1i >= 0 && st.g2i >= 0 && st.g1i != st.g2i && st.g1v <= st.g2v && st.g1v + nq2 >= 0,
+                     "top-2 of a row is not two distinct, ordered train rows");
           Knn2 out;
           out.j0 = st.g1i;
           out.j1 = st.g2i;
