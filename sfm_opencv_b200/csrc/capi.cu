@@ -32,6 +32,9 @@ cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pa
                                 float dist_floor, float gate_mult, const float* min_dist,
                                 const int64_t* offsets, sfm_match_t* out, int64_t out_cap,
                                 cudaStream_t s);
+cudaError_t launch_commit_rows(const uint8_t* desc, const int32_t* img_row0, const int32_t* img_n,
+                               int first_img, int n_img, int row_begin, int row_end, int32_t* norm,
+                               int32_t* ckey, int32_t* gmin8, uint32_t* flags, cudaStream_t s);
 cudaError_t launch_knn_to_float(const Knn2* knn, int64_t n, sfm_knn2_t* out, cudaStream_t s);
 cudaError_t launch_build_items(const int2* ordoff, int n_pairs, const PairDesc* pairs, int qblock,
                                int2* items, cudaStream_t s);
@@ -120,7 +123,7 @@ struct sfm_ctx {
   EncodeTiledFn encode = nullptr;
 
   // descriptor bank (padded rows)
-  DevBuf desc, norm, ckey, gmin8, flags, stage;
+  DevBuf desc, norm, ckey, gmin8, flags, stage, img_tab;   // img_tab: row offsets + counts (device)
   std::vector<int32_t> img_n, img_row0;
   std::vector<uint8_t> img_ok;                 // image rows + norms + keys are in the bank
   int imgs_missing = 0;                        // images of the current layout not yet uploaded / committed
@@ -266,7 +269,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->pairs,
+  DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_tab, &ctx->pairs,
                     &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
@@ -388,6 +391,11 @@ static int bank_layout(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim, 
   CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
   CK(ctx->gmin8.ensure(static_cast<size_t>(rows) / 8 * 4 + 64));
   CK(ctx->flags.ensure(4));
+  CK(ctx->img_tab.ensure(8 * static_cast<size_t>(n_img)));
+  CK(cudaMemcpyAsync(ctx->img_tab.p, ctx->img_row0.data(), 4 * static_cast<size_t>(n_img),
+                     cudaMemcpyHostToDevice, up));
+  CK(cudaMemcpyAsync(ctx->img_tab.as<int32_t>() + n_img, ctx->img_n.data(), 4 * static_cast<size_t>(n_img),
+                     cudaMemcpyHostToDevice, up));
   CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kDim, up));
   CK(cudaMemsetAsync(ctx->flags.p, 0, 4, up));
   ctx->bank_binary = false;
@@ -512,8 +520,14 @@ int sfm_bank_commit(sfm_ctx* ctx, int first_img, int n_img) {
   if (rc) return rc;
   if (n_img == 0) return SFM_OK;
   CK(cudaSetDevice(ctx->device));
-  rc = pack_images(ctx, first_img, n_img, nullptr, false, ctx->stream, false);
-  if (rc) return rc;
+  const int last = first_img + n_img - 1;
+  const int n_all = static_cast<int>(ctx->img_n.size());
+  const int row_begin = ctx->img_row0[first_img];
+  const int row_end = ctx->img_row0[last] + (ctx->img_n[last] + kRowPad - 1) / kRowPad * kRowPad;
+  CK(launch_commit_rows(ctx->desc.as<uint8_t>(), ctx->img_tab.as<int32_t>(), ctx->img_tab.as<int32_t>() + n_all,
+                        first_img, n_img, row_begin, row_end, ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(),
+                        ctx->gmin8.as<int32_t>(), ctx->flags.as<uint32_t>(), ctx->stream));
+  ctx->launches += 2;
   return finish_pack(ctx, first_img, n_img, ctx->stream);
 }
 

@@ -83,6 +83,56 @@ __global__ void group_min_kernel(const int32_t* __restrict__ norm, int row0, int
   gmin8[row0 / 8 + g] = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
 }
 
+// Rows that arrived from another GPU (sfm_bank_commit): norms, keys and sentinels of a whole range
+// of IMAGES in one launch -- one warp per bank row, the row's image found by binary search in the
+// row-offset table (175 images of an 8-GPU all-gather would otherwise cost 525 tiny launches).
+__global__ void commit_rows_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ img_row0,
+                                   const int32_t* __restrict__ img_n, int first_img, int n_img,
+                                   int row_begin, int row_end, int32_t* __restrict__ norm,
+                                   int32_t* __restrict__ ckey, uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int row = row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= row_end) return;
+  int lo = first_img, hi = first_img + n_img - 1;          // last image whose first row is <= row
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (img_row0[mid] <= row) lo = mid; else hi = mid - 1;
+  }
+  const int r = row - img_row0[lo];
+  int s = kNormPad;
+  if (r < img_n[lo]) {
+    const uint32_t packed = reinterpret_cast<const uint32_t*>(desc)[static_cast<size_t>(row) * 32 + lane];
+    s = __dp4a(packed, packed, 0u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (s > kMaxNorm && lane == 0) atomicOr(flags, kFlagNorm);
+  }
+  if (lane == 0) {
+    norm[row] = s;
+    ckey[row] = (s << kColBits) | (r & ((1 << kColBits) - 1));
+  }
+}
+
+__global__ void group_min_range_kernel(const int32_t* __restrict__ norm, int row_begin, int row_end,
+                                       int32_t* __restrict__ gmin8) {
+  const int g = row_begin / 8 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 8 >= row_end) return;
+  const int4 a = *reinterpret_cast<const int4*>(norm + g * 8);
+  const int4 b = *reinterpret_cast<const int4*>(norm + g * 8 + 4);
+  gmin8[g] = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
+}
+
+cudaError_t launch_commit_rows(const uint8_t* desc, const int32_t* img_row0, const int32_t* img_n,
+                               int first_img, int n_img, int row_begin, int row_end, int32_t* norm,
+                               int32_t* ckey, int32_t* gmin8, uint32_t* flags, cudaStream_t s) {
+  const int rows = row_end - row_begin;
+  if (rows <= 0) return cudaSuccess;
+  commit_rows_kernel<<<(rows + 3) / 4, 128, 0, s>>>(desc, img_row0, img_n, first_img, n_img, row_begin,
+                                                    row_end, norm, ckey, flags);
+  group_min_range_kernel<<<(rows / 8 + 127) / 128, 128, 0, s>>>(norm, row_begin, row_end, gmin8);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------- filter
 __device__ __forceinline__ bool ratio_fails(float d0, float d1, double ratio) {
   // `knn[i][0].distance > 0.6 * knn[i][1].distance`: float promoted to double (:884, :900)
