@@ -59,10 +59,10 @@ namespace sfm {
 #endif
 
 // -DSFM_CHECKS: protocol / bounds assertions in the kernel (compute-sanitizer is closed on the GPU
-// pool this was developed on, profiles/r2_sanitizer_unavailable.txt): work-item tables, TMEM and
+// pool this was developed on, profiles/rnd2_sanitizer_unavailable.txt): work-item tables, TMEM and
 // shared-memory ring addresses, result rows and the tag discipline of the bound exchange are checked
 // on the device and trap with a message.  The GPU tests are run once against this build
-// (tools/variants.py build chk:-DSFM_CHECKS; profiles/r2_checks_build_tests.txt).
+// (tools/variants.py build chk:-DSFM_CHECKS; profiles/rnd2_checks_build_tests.txt).
 #ifdef SFM_CHECKS
 #define SFM_ASSERT(cond, what)                                                                  \
   do {                                                                                          \
