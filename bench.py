@@ -180,10 +180,17 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------- extras
+L2_BYTES = 126e6
+
+
 def _roof(bytes_, ms, hbm_gbs, peak_src, **kw):
     gbs = bytes_ / (ms * 1e-3) / 1e9
-    return dict({"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
-                 "peak_source": peak_src}, **kw)
+    out = dict({"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs,
+                "peak_source": peak_src}, **kw)
+    if bytes_ < L2_BYTES:
+        # the repeated launches of the timing loop re-use buffers that fit in the 126 MB L2: not an HBM number
+        out.update(frac=None, note=f"working set {bytes_ / 1e6:.0f} MB fits in L2: repeated launches are L2-resident")
+    return out
 
 
 def extra_pair65536(ctx, n=65536, cpu=True):
@@ -777,7 +784,7 @@ def run_geometry(args, rank, local_rank, world):
                         "h2d_bytes_per_step": int(sc["xy"].nbytes), "d2h_bytes_per_step": int(28 * n),
                         "api": "sfm_triangulate_batch(pinned host xy -> pinned host X4 + xyz) on every rank's point range"},
                 "residuals": {"obs_per_s": n * V / (res_ms * 1e-3), "ms": res_ms,
-                              "roofline": _roof(32 * (e - s) * V + 24 * n, res_ms, hbm_gbs, peak_src, per="rank 0"),
+                              "roofline": _roof(32 * (e - s) * V + 24 * (e - s), res_ms, hbm_gbs, peak_src, per="rank 0"),
                               "e2e_obs_per_s": n * V / res_e2e, "e2e_ms": res_e2e * 1e3,
                               "huber_cost_sum_over_ranks": cost_sum, "huber_cost_single_gpu": c_all,
                               "rel_diff": abs(cost_sum - c_all) / abs(c_all)}}
