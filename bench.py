@@ -8,14 +8,19 @@ Workload (BASELINE.json config 3): synthetic exhaustive all-pairs SIFT matching,
 200 images x 8192 integer-valued 128-d descriptors = 19,900 pairs (i<j, query=i, train=j),
 kNN k=2 + Lowe ratio + min-distance gate exactly as match_features()
 (OpenCV_SFM/NViewReconstuct.cpp:873-913).  One "step" = one pass over all 19,900 pairs.
-Pairs are sharded over ranks in contiguous blocks (no data-path collective); total work is
-fixed by the config, so the scaling label is "strong".
+Pairs are sharded over ranks in contiguous cost-balanced blocks (no data-path collective on
+results); total work is fixed by the config, so the scaling label is "strong".
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with descriptors resident in HBM;
 `e2e` = pairs/s through the reference-facing call (host CV_32F descriptor matrices in,
 host DMatch lists out, copies inside the timed region).  With N > 1 ranks every image crosses
 PCIe once: rank r uploads its 1/N slice of the images, and the packed u8 rows are all-gathered
-over NVLink (NCCL) straight into every rank's bank (sfm_bank_layout / _upload_range / _commit).
+over NVLink (NCCL) straight into every rank's bank.  The image list is cut into --stages regions
+whose upload / exchange / commit are queued on the library's upload stream while ONE
+sfm_match_pairs call matches the pairs in the order their images arrive.  --exchange push
+(default): every rank pushes its rows into the peers' banks with the copy engines over NVLink and
+raises flags in their mailboxes (sfm_peer_*, sfm_bank_push_range_async: no collective, no SMs);
+--exchange nccl: an in-place NCCL all-gather per region on the upload stream.
 
 Other workloads (their own metric; lines kept under profiles/):
     --workload pair65536   BASELINE config 4: one 65536 x 65536 pair, query rows sharded over the
@@ -173,7 +178,9 @@ def workload_config(args, world):
                         f"x 128 u8-valued descriptors, {n_pairs} pairs, kNN k=2 + ratio 0.6 + "
                         f"5*max(min_dist,10) gate (BASELINE.json configs[2])",
             "pairs": n_pairs, "images": args.images, "desc_per_image": args.desc,
-            "sharding": f"contiguous pair blocks over {world} rank(s), no collective",
+            "sharding": (f"contiguous pair blocks over {world} rank(s), no collective" if world == 1 else
+                         f"{world} ranks; per arrival stage of the staged upload ({max(1, args.stages)} image regions) "
+                         "contiguous cost-balanced pair blocks; no collective on results"),
             "l2": f"descriptor bank {args.images * args.desc * 128 / 1e6:.0f} MB "
                   f"{'>' if args.images * args.desc * 128 > 126e6 else '<='} 126 MB L2; "
                   "no explicit flush"}
@@ -456,7 +463,7 @@ class Ranks:
 
 def run_b200(args, rank, local_rank, world):
     import sfm_opencv_b200 as sfm
-    from sfm_opencv_b200.sharding import shard_pairs
+    from sfm_opencv_b200.sharding import image_regions, shard_pairs_staged, staged_image_ranges
     rk = Ranks(rank, local_rank, world)
     torch, dist = rk.torch, rk.dist
     barrier, allmax, allsum = rk.barrier, rk.allmax, rk.allsum
@@ -468,8 +475,16 @@ def run_b200(args, rank, local_rank, world):
     bank = make_bank(args.images, args.desc)                 # u8, every rank (replicated bank)
     pairs = all_pairs(args.images)
     n_desc = [len(b) for b in bank]
-    lo, hi = shard_pairs(pairs, n_desc, world)[rank]
-    my_pairs = pairs[lo:hi]
+    pairs_np = np.asarray(pairs, np.int32)                   # the pair list as a caller's int array
+    if world == 1:
+        regions = None
+        my_pairs = pairs_np
+    else:
+        # staged layout (see the e2e block below): image regions in arrival order, and pair shards
+        # that give every rank its share of every arrival stage
+        regions = staged_image_ranges(args.images, world, max(1, args.stages))
+        mine_idx = shard_pairs_staged(pairs, n_desc, world, image_regions(args.images, regions))[rank]
+        my_pairs = pairs_np[mine_idx]
     n_pairs = len(pairs)
 
     # ---- value: descriptors resident in HBM, result lists left on the device ------------
@@ -527,45 +542,83 @@ def run_b200(args, rank, local_rank, world):
             ctx.upload_descriptors(host_f32, overlap=True)   # H2D overlaps the matching kernels
             return ctx.match_pairs(my_pairs, copy=False)
     else:
-        # every image crosses PCIe ONCE per step: this rank uploads images [i0, i1), the packed u8
-        # rows are all-gathered over NVLink into every rank's bank, the received images are committed
-        i0, i1 = shard_range(args.images, world)[rank]
+        # every image crosses PCIe ONCE per step, and the exchange is overlapped with matching:
+        # the image list is cut into `--stages` regions; per region this rank uploads its part
+        # (1/N of the region), the packed u8 rows are all-gathered over NVLink in place on the
+        # library's upload stream, the peers' parts are committed -- all queued without host
+        # synchronisation -- and ONE sfm_match_pairs call visits the pairs in arrival order, each
+        # launch waiting only for the images it reads (sfm_bank_*_async, include/sfm_b200.h)
+        mine = [regions[k][rank] for k in range(len(regions))]          # (first image, count) per region
         host_f32 = []
-        for k in range(i0, i1):
-            a = ctx.pinned_empty(bank[k].shape, np.float32, f"desc{k}")
-            a[...] = bank[k]
-            host_f32.append(a)
-        h2d = sum(a.nbytes for a in host_f32) + 8 * len(my_pairs)
+        for first, count in mine:
+            part = []
+            for k in range(first, first + count):
+                a = ctx.pinned_empty(bank[k].shape, np.float32, f"desc{k}")
+                a[...] = bank[k]
+                part.append(a)
+            host_f32.append(part)
+        h2d = sum(a.nbytes for part in host_f32 for a in part) + 8 * len(my_pairs)
         ctx.bank_layout(n_desc)
-        spans = []                                           # bank row range of every rank's slice
-        for r, (a0, a1) in enumerate(shard_range(args.images, world)):
-            if a1 > a0:
-                r0, _ = ctx.bank_image_rows(a0)
-                rl, nl = ctx.bank_image_rows(a1 - 1)
-                spans.append((r0, rl + nl))
-            else:
-                spans.append((0, 0))
-        equal = len({b - a for a, b in spans}) == 1 and all(spans[r][0] == r * (spans[0][1] - spans[0][0]) for r in range(world))
-        nvlink = sum(b - a for r, (a, b) in enumerate(spans) if r != rank) * 128
-        e2e_api = ("sfm_bank_layout + sfm_bank_upload_range(this rank's 1/N of the images, pinned CV_32F) + "
-                   f"NCCL {'all_gather_into_tensor (in place)' if equal else 'broadcast per rank'} of the packed u8 rows "
-                   "over NVLink + sfm_bank_commit + sfm_match_pairs + sfm_fetch_matches")
+        spans = []                                           # per region: bank row range of every rank's part
+        for row in regions:
+            sp = []
+            for first, count in row:
+                if count > 0:
+                    r0, _ = ctx.bank_image_rows(first)
+                    rl, nl = ctx.bank_image_rows(first + count - 1)
+                    sp.append((r0, rl + nl))
+                else:
+                    sp.append((0, 0))
+            spans.append(sp)
+        equal = all(len({b - a for a, b in sp}) == 1 and sp[0][1] > sp[0][0] for sp in spans)
+        nvlink = sum(b - a for sp in spans for r, (a, b) in enumerate(sp) if r != rank) * 128
+        push = args.exchange == "push"
+        if push:
+            # peer handles (CUDA IPC) once, any transport: here torch.distributed's object gather
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_export())
+            ctx.peer_connect(rank, handles)
+            exch = ("sfm_bank_push_range_async: copy-engine pushes of the packed u8 rows into every peer's bank over "
+                    "NVLink (CUDA IPC peer memory) + mailbox flags (stream memory operations), no collective, no SMs")
+        else:
+            up_stream = ctx.upload_stream_torch()
+            exch = (f"NCCL {'all_gather_into_tensor (in place)' if equal else 'broadcast per rank'} of the packed u8 "
+                    "rows over NVLink on the upload stream")
+        e2e_api = (f"sfm_bank_layout_async + per region ({len(regions)} regions): sfm_bank_upload_range_async(this "
+                   f"rank's 1/N of the region, pinned CV_32F) + {exch} + commit of the peers' parts; then ONE "
+                   "sfm_match_pairs (pairs visited in arrival order, matching overlaps the later regions) + "
+                   "sfm_fetch_matches")
+        step_tag = [0]
 
         def e2e_step():
-            ctx.bank_layout(n_desc)
-            ctx.bank_upload_range(i0, host_f32)
+            ctx.bank_layout(n_desc, overlap=True)
+            if push:
+                step_tag[0] += 1
+                tag = step_tag[0]
+                ctx.bank_ready(tag)
+                for k, row in enumerate(regions):
+                    first, count = row[rank]
+                    ctx.bank_upload_range(first, host_f32[k], overlap=True)
+                    ctx.bank_push_range(first, count, k, tag)
+                    for d in range(1, world):
+                        r = (rank - d) % world               # the peer that pushes to this rank first
+                        ctx.bank_pull_commit(r, row[r][0], row[r][1], k, tag)
+                return ctx.match_pairs(my_pairs, copy=False)
             bt = ctx.bank_as_torch()
-            if equal:
-                dist.all_gather_into_tensor(bt[:spans[-1][1]], bt[spans[rank][0]:spans[rank][1]])
-            else:
-                for r, (a, b) in enumerate(spans):
-                    if b > a:
-                        dist.broadcast(bt[a:b], src=r)
-            torch.cuda.current_stream().synchronize()
-            if i0 > 0:
-                ctx.bank_commit(0, i0)
-            if i1 < args.images:
-                ctx.bank_commit(i1, args.images - i1)
+            for k, row in enumerate(regions):
+                first, count = row[rank]
+                ctx.bank_upload_range(first, host_f32[k], overlap=True)
+                sp = spans[k]
+                with torch.cuda.stream(up_stream):
+                    if equal:
+                        dist.all_gather_into_tensor(bt[sp[0][0]:sp[-1][1]], bt[sp[rank][0]:sp[rank][1]])
+                    else:
+                        for r, (a, b) in enumerate(sp):
+                            if b > a:
+                                dist.broadcast(bt[a:b], src=r)
+                r_first, r_end = row[0][0], row[-1][0] + row[-1][1]
+                ctx.bank_commit(r_first, first - r_first, overlap=True)
+                ctx.bank_commit(first + count, r_end - first - count, overlap=True)
             return ctx.match_pairs(my_pairs, copy=False)
 
     for _ in range(2):
@@ -579,6 +632,9 @@ def run_b200(args, rank, local_rank, world):
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     barrier()
+    if world > 1 and args.exchange == "push":
+        ctx.peer_disconnect()                                # unmap the peers' banks before anyone frees one
+        barrier()
     e2e_matches = int(allsum(len(m.flat)))
     e2e_s = allmax(e2e_s)
     e2e_val = n_pairs * args.steps / e2e_s
@@ -809,6 +865,10 @@ def main():
     ap.add_argument("--points", type=int, default=4_000_000)
     ap.add_argument("--views", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="N > 1: how the packed rows travel GPU to GPU (copy-engine pushes + flags, or NCCL all-gather)")
+    ap.add_argument("--stages", type=int, default=2,
+                    help="N > 1: regions of the image list whose upload + NVLink exchange is pipelined with matching")
     args = ap.parse_args()
 
     world = env_int("WORLD_SIZE", 1)

@@ -26,6 +26,11 @@ int main(int argc, char** argv) {
                        (const void*)sfm_bank_layout, (const void*)sfm_bank_upload_range,
                        (const void*)sfm_bank_commit, (const void*)sfm_bank_image_rows,
                        (const void*)sfm_bank_rows_dev, (const void*)sfm_bank_copy_peer,
+                       (const void*)sfm_bank_layout_async, (const void*)sfm_bank_upload_range_async,
+                       (const void*)sfm_bank_commit_async, (const void*)sfm_upload_stream,
+                       (const void*)sfm_peer_export, (const void*)sfm_peer_connect,
+                       (const void*)sfm_peer_disconnect, (const void*)sfm_bank_ready_async,
+                       (const void*)sfm_bank_push_range_async, (const void*)sfm_bank_pull_commit_async,
                        (const void*)sfm_match_rows_begin, (const void*)sfm_match_rows_finish,
                        (const void*)sfm_ba_create, (const void*)sfm_ba_evaluate, (const void*)sfm_ba_destroy};
   size_t n = sizeof fns / sizeof fns[0], i;

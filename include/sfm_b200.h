@@ -161,6 +161,69 @@ SFM_API void* sfm_bank_rows_dev(sfm_ctx* ctx, int64_t* n_rows);
  * dst's bank and commits them.  Both banks must have the same layout. */
 SFM_API int sfm_bank_copy_peer(sfm_ctx* dst, sfm_ctx* src, int first_img, int n_img);
 
+/* ---- staged arrival (N GPUs, upload and exchange overlapped with matching) ---------------
+ *
+ * The same three steps, queued on the context's upload stream without host synchronisation;
+ * the caller enqueues its own peer transfers on that stream between them:
+ *
+ *   sfm_bank_layout_async(ctx, n_img, n_desc, 128)
+ *   for every region k of the image list (2-4 regions):
+ *     sfm_bank_upload_range_async(ctx, my part of region k)      host -> bank (pinned memory)
+ *     <all-gather of region k on sfm_upload_stream(ctx)>          e.g. ncclAllGather in place
+ *     sfm_bank_commit_async(ctx, the peers' parts of region k)
+ *   sfm_match_pairs(...)                                          ONE call, as usual
+ *
+ * Every asynchronous range call is one arrival stage.  sfm_match_pairs visits the pairs in
+ * the order their images arrive (results stay in caller order) and makes every kernel launch
+ * wait only for the images it reads, so the pairs of region 0 are matched while regions 1..
+ * are still crossing PCIe / NVLink; it also reports the validation result of the whole upload
+ * (SFM_E_NOT_INTEGRAL / SFM_E_RANGE).  Host arrays must stay valid until it returns.
+ * match_features_for_all (NViewReconstuct.cpp:857-870) has no cross-pair state, so the
+ * visiting order is free. */
+SFM_API int sfm_bank_layout_async(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim);
+SFM_API int sfm_bank_upload_range_async(sfm_ctx* ctx, int first_img, int n_img,
+                                        const void* const* desc, int elem_bytes);
+SFM_API int sfm_bank_commit_async(sfm_ctx* ctx, int first_img, int n_img);
+/* The upload stream as a cudaStream_t (opaque here): work a caller enqueues on it is ordered
+ * with the asynchronous uploads and commits. */
+SFM_API void* sfm_upload_stream(sfm_ctx* ctx);
+
+/* ---- peer exchange without a collective: push over NVLink, flags in peer memory ------------
+ *
+ * An NCCL all-gather needs SMs, and the persistent kNN kernel owns every SM for the length of a
+ * launch, so a collective for region k+1 queues behind the matching of region k.  Here every
+ * rank PUSHES its packed rows into the peers' banks with the copy engines (cudaMemcpyAsync to
+ * peer memory mapped through CUDA IPC, or plain peer pointers inside one process) and raises a
+ * flag in the peers' mailboxes; the receivers wait on their own mailbox with stream memory
+ * operations (SFM_PEER_FLAGS=kernel: 1-thread kernels).  No SMs, no host synchronisation.
+ *
+ *   once (same layout on every rank):
+ *     sfm_bank_layout(ctx, ...); sfm_peer_export(ctx, h); <exchange the handles, any transport>;
+ *     sfm_peer_connect(ctx, my_rank, n_ranks, all_handles)
+ *   every step, tag = 1, 2, 3, ... (the same on every rank):
+ *     sfm_bank_layout_async(ctx, ...); sfm_bank_ready_async(ctx, tag)
+ *     for every region k:
+ *       sfm_bank_upload_range_async(ctx, my part of region k)
+ *       sfm_bank_push_range_async(ctx, my part, k, tag)      waits for each peer's READY(tag)
+ *       for every peer r: sfm_bank_pull_commit_async(ctx, r, r's part of region k, k, tag)
+ *     sfm_match_pairs(...)
+ * A peer may run ahead by less than one step: its pushes for step tag+1 wait for this rank's
+ * READY(tag+1), which is raised behind this rank's own layout of step tag+1.
+ * The bank must not be re-allocated between export and use (same image sizes every step).
+ * Host arrays of the asynchronous calls should be pinned (sfm_host_alloc): with a pageable
+ * source cudaMemcpyAsync blocks the host until the stream reaches the copy -- behind a wait for
+ * a peer's flag, and forever if the same host thread is the one that has yet to raise it. */
+#define SFM_PEER_HANDLE_BYTES 160
+SFM_API int sfm_peer_export(sfm_ctx* ctx, void* handle /* SFM_PEER_HANDLE_BYTES */);
+SFM_API int sfm_peer_connect(sfm_ctx* ctx, int my_rank, int n_ranks,
+                             const void* handles /* n_ranks x SFM_PEER_HANDLE_BYTES, rank order */);
+SFM_API int sfm_peer_disconnect(sfm_ctx* ctx);
+SFM_API int sfm_bank_ready_async(sfm_ctx* ctx, uint32_t tag);
+/* slot: 0..14, the region's index -- one flag per (slot, source rank) in every mailbox. */
+SFM_API int sfm_bank_push_range_async(sfm_ctx* ctx, int first_img, int n_img, int slot, uint32_t tag);
+SFM_API int sfm_bank_pull_commit_async(sfm_ctx* ctx, int src_rank, int first_img, int n_img, int slot,
+                                       uint32_t tag);
+
 /* For every pair p: knnMatch(desc[pair_q[p]], desc[pair_t[p]], k=2) with NORM_L2,
  * then the reference's two filter passes (NViewReconstuct.cpp:880-908):
  *   pass 1  min_dist = min{ d0 : !(d0 > ratio*d1) }           (double compare)

@@ -62,6 +62,16 @@ SYMBOLS = {
     "sfm_bank_image_rows": (_i, [_vp, _i, _pi64, _pi64]),
     "sfm_bank_rows_dev": (_vp, [_vp, _pi64]),
     "sfm_bank_copy_peer": (_i, [_vp, _vp, _i, _i]),
+    "sfm_bank_layout_async": (_i, [_vp, _i, _pi, _i]),
+    "sfm_bank_upload_range_async": (_i, [_vp, _i, _i, C.POINTER(_vp), _i]),
+    "sfm_bank_commit_async": (_i, [_vp, _i, _i]),
+    "sfm_upload_stream": (_vp, [_vp]),
+    "sfm_peer_export": (_i, [_vp, _vp]),
+    "sfm_peer_connect": (_i, [_vp, _i, _i, _vp]),
+    "sfm_peer_disconnect": (_i, [_vp]),
+    "sfm_bank_ready_async": (_i, [_vp, C.c_uint32]),
+    "sfm_bank_push_range_async": (_i, [_vp, _i, _i, _i, C.c_uint32]),
+    "sfm_bank_pull_commit_async": (_i, [_vp, _i, _i, _i, _i, C.c_uint32]),
     "sfm_match_rows_begin": (_i, [_vp, _pi, _pi, _pi, _pi, _i, _d, _pf]),
     "sfm_match_rows_finish": (_i, [_vp, _pf, _f, _f, _pi64, _vp]),
     "sfm_ba_create": (_i, [_vp, _i, _i64, _pi, _pi, _pf, _i64, C.POINTER(_vp)]),

@@ -54,6 +54,14 @@ def _ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
+def _pair_array(pairs) -> np.ndarray:
+    """[n,2] int32 view of a pair list.  An int32 ndarray passes through untouched (a caller's
+    std::vector<int> pair list costs nothing); a Python list of tuples costs ~0.4 us per pair."""
+    if isinstance(pairs, np.ndarray):
+        return np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+    return np.asarray(list(pairs), np.int32).reshape(-1, 2)
+
+
 class Context:
     """One sfm_ctx: one GPU, one host thread."""
 
@@ -144,15 +152,27 @@ class Context:
         self.n_desc = [int(x) for x in n]
 
     # ------------------------------------------------------------------ sharded upload
-    def bank_layout(self, n_desc):
+    def bank_layout(self, n_desc, overlap: bool = False):
         """Lays out the bank for len(n_desc) images without data (sfm_bank_layout): the same call
         on every GPU; images then arrive by bank_upload_range (from this host) or from a peer
-        (all-gather into bank_rows_dev / bank_copy_peer) + bank_commit."""
+        (all-gather into bank_rows_dev / bank_copy_peer) + bank_commit.
+        overlap=True (here and in bank_upload_range / bank_commit): the staged form -- everything
+        is queued on the upload stream (upload_stream_torch) and the next match_pairs overlaps
+        matching with the arrival of the later ranges (sfm_bank_*_async)."""
         n = np.ascontiguousarray(n_desc, np.int32)
-        self._check(self._lib.sfm_bank_layout(self._h, len(n), _ptr(n, C.c_int32), 128))
+        fn = self._lib.sfm_bank_layout_async if overlap else self._lib.sfm_bank_layout
+        self._check(fn(self._h, len(n), _ptr(n, C.c_int32), 128))
         self.n_desc = [int(x) for x in n]
+        self._pending_upload = []
 
-    def bank_upload_range(self, first_img: int, descs):
+    def upload_stream_torch(self):
+        """The context's upload stream as a torch.cuda.ExternalStream: collectives issued under
+        `with torch.cuda.stream(...)` are ordered with the asynchronous uploads and commits."""
+        import torch
+        ptr = self._lib.sfm_upload_stream(self._h)
+        return torch.cuda.ExternalStream(int(ptr), device=torch.device("cuda", self.device))
+
+    def bank_upload_range(self, first_img: int, descs, overlap: bool = False):
         """Host rows of images first_img .. first_img + len(descs) - 1 -> their bank rows."""
         descs = [np.ascontiguousarray(d) for d in descs]
         if not descs:
@@ -164,11 +184,49 @@ class Context:
             if d.ndim != 2 or d.shape != (self.n_desc[first_img + k], 128):
                 raise SfmError(_capi.SFM_E_INVALID, "descriptor matrix does not match the bank layout")
         ptrs = (C.c_void_p * len(descs))(*[d.ctypes.data for d in descs])
-        self._check(self._lib.sfm_bank_upload_range(self._h, first_img, len(descs), ptrs,
-                                                    1 if is_u8 else 4))
+        if overlap:
+            if not isinstance(getattr(self, "_pending_upload", None), list):
+                self._pending_upload = []
+            self._pending_upload.append(descs)       # keep the host arrays alive
+            self._check(self._lib.sfm_bank_upload_range_async(self._h, first_img, len(descs), ptrs,
+                                                              1 if is_u8 else 4))
+        else:
+            self._check(self._lib.sfm_bank_upload_range(self._h, first_img, len(descs), ptrs,
+                                                        1 if is_u8 else 4))
 
-    def bank_commit(self, first_img: int, n_img: int):
-        self._check(self._lib.sfm_bank_commit(self._h, first_img, n_img))
+    def bank_commit(self, first_img: int, n_img: int, overlap: bool = False):
+        fn = self._lib.sfm_bank_commit_async if overlap else self._lib.sfm_bank_commit
+        self._check(fn(self._h, first_img, n_img))
+
+    # ------------------------------------------------------------------ peer push exchange
+    PEER_HANDLE_BYTES = 160
+
+    def peer_export(self) -> bytes:
+        """Handle of this context's bank and mailbox (sfm_peer_export; after bank_layout)."""
+        buf = (C.c_uint8 * self.PEER_HANDLE_BYTES)()
+        self._check(self._lib.sfm_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, my_rank: int, handles):
+        """handles: the peer_export() bytes of every rank, in rank order (own entry included)."""
+        blob = b"".join(handles)
+        if len(blob) != self.PEER_HANDLE_BYTES * len(handles):
+            raise SfmError(_capi.SFM_E_INVALID, "malformed peer handle list")
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.sfm_peer_connect(self._h, my_rank, len(handles), buf))
+
+    def peer_disconnect(self):
+        self._check(self._lib.sfm_peer_disconnect(self._h))
+
+    def bank_ready(self, tag: int):
+        self._check(self._lib.sfm_bank_ready_async(self._h, tag & 0xFFFFFFFF))
+
+    def bank_push_range(self, first_img: int, n_img: int, slot: int, tag: int):
+        self._check(self._lib.sfm_bank_push_range_async(self._h, first_img, n_img, slot, tag & 0xFFFFFFFF))
+
+    def bank_pull_commit(self, src_rank: int, first_img: int, n_img: int, slot: int, tag: int):
+        self._check(self._lib.sfm_bank_pull_commit_async(self._h, src_rank, first_img, n_img, slot,
+                                                         tag & 0xFFFFFFFF))
 
     def bank_image_rows(self, img: int):
         """(first bank row, padded row count) of an image; rows of consecutive images are contiguous."""
@@ -204,7 +262,7 @@ class Context:
     def match_rows_begin(self, pairs, q_first, q_count, ratio=RATIO):
         """Pass 1 of match_features over query rows [q_first[p], q_first[p] + q_count[p]) of every
         pair: returns this shard's min_dist per pair (reduce with MIN over the shards)."""
-        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        pairs = _pair_array(pairs)
         pq = np.ascontiguousarray(pairs[:, 0])
         pt = np.ascontiguousarray(pairs[:, 1])
         qf = np.ascontiguousarray(q_first, np.int32)
@@ -264,7 +322,7 @@ class Context:
         Two C-ABI calls: sfm_match_pairs sizes the result (offsets), sfm_fetch_matches copies
         exactly offsets[n_pairs] matches into a pinned buffer.  With copy=False the returned
         arrays are views of that buffer and are overwritten by the next call."""
-        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        pairs = _pair_array(pairs)
         n_pairs = pairs.shape[0]
         pq = np.ascontiguousarray(pairs[:, 0])
         pt = np.ascontiguousarray(pairs[:, 1])
@@ -339,7 +397,7 @@ class Context:
     def match_pairs_resident(self, pairs, ratio=RATIO, dist_floor=DIST_FLOOR,
                              gate_mult=GATE_MULT):
         """Device-resident timing hook: returns (total_matches, knn_kernel_ms, total_ms)."""
-        pairs = np.asarray(list(pairs), np.int32).reshape(-1, 2)
+        pairs = _pair_array(pairs)
         pq = np.ascontiguousarray(pairs[:, 0])
         pt = np.ascontiguousarray(pairs[:, 1])
         total = C.c_int64(0)

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -96,6 +97,9 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+constexpr int kPeerMaxRanks = 64, kPeerSlots = 15;     // mailbox rows: READY + 15 DATA slots
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -112,7 +116,26 @@ struct sfm_ctx {
   // their own stream, one event per image; matching kernels wait only for the images they read
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> img_ev;
+  // arrival bookkeeping of an asynchronous upload: which event says "image i is resident"
+  // (a committed range shares the event of its last image), in which order the events were
+  // recorded (epoch), and the arrival stage of the image -- one stage per asynchronous range
+  // call, so that sfm_match_pairs can visit the pairs in the order their images arrive
+  std::vector<int32_t> img_evid, img_stage;
+  std::vector<int64_t> img_epoch;
+  int64_t epoch = 0;
+  int32_t next_stage = 0;
   cudaEvent_t upload_done = nullptr;
+  // peer exchange over NVLink without NCCL and without SMs (sfm_peer_*): every rank PUSHES its
+  // packed rows into the peers' banks with the copy engines and raises a flag in the peers'
+  // mailboxes; stream memory operations (or 1-thread kernels) wait on the local mailbox
+  DevBuf mailbox;                        // uint32 [1 + kPeerSlots][kPeerMaxRanks]: READY row, DATA rows
+  int peer_rank = -1, peer_n = 0;
+  std::vector<uint8_t*> peer_bank;       // the peers' bank rows / mailboxes, mapped into this process
+  std::vector<uint32_t*> peer_mail;
+  std::vector<uint8_t> peer_ipc;         // 1: mapping came from cudaIpcOpenMemHandle (close it)
+  void* peer_bank_exported = nullptr;    // desc.p at export time: a re-allocation breaks the mapping
+  bool peer_memops = true;               // cuStreamWriteValue32 / WaitValue32; false: flag kernels
+  StreamValueFn stream_write = nullptr, stream_wait = nullptr;
   uint32_t* h_flags = nullptr;          // pinned: validation flags of the pending upload
   bool upload_pending = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -131,6 +154,7 @@ struct sfm_ctx {
   std::vector<PairDesc> h_pairs;
   DevBuf ordoff;
   std::vector<int32_t> h_order;                // processing order of the pairs (L2 blocking)
+  std::vector<int32_t> h_bucket, h_key;        // counting sort of the pairs by block key
   std::vector<std::pair<int64_t, int>> h_groups;   // per L2 block: first work item, last image read
   int64_t bank_rows = 0;
   bool bank_ready = false;
@@ -244,6 +268,16 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     return bail(SFM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  {
+    void *fw = nullptr, *fq = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fw, cudaEnableDefault, &qres) == cudaSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue32", &fq, cudaEnableDefault, &qres) == cudaSuccess) {
+      ctx->stream_write = reinterpret_cast<StreamValueFn>(fw);
+      ctx->stream_wait = reinterpret_cast<StreamValueFn>(fq);
+    }
+    const char* pf = getenv("SFM_PEER_FLAGS");         // "kernel": 1-thread flag kernels instead
+    ctx->peer_memops = ctx->stream_write && ctx->stream_wait && !(pf && strcmp(pf, "kernel") == 0);
+  }
   if (const char* m = getenv("SFM_KNN_MODE")) {
     // A/B switch of the exact epilogues (0 = unfiltered, 1 = filtered; identical results);
     // anything else exists only in -DSFM_EXPERIMENTS builds and is refused here otherwise
@@ -264,6 +298,8 @@ void sfm_destroy(sfm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  sfm_peer_disconnect(ctx);
+  ctx->mailbox.release();
   for (auto& ev : ctx->img_ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->upload_done) cudaEventDestroy(ctx->upload_done);
@@ -377,6 +413,11 @@ static int bank_layout(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim, 
   ctx->img_row0.resize(n_img);
   ctx->img_ok.assign(n_img, 0);
   ctx->imgs_missing = n_img;
+  ctx->img_evid.assign(n_img, 0);
+  ctx->img_stage.assign(n_img, 0);
+  ctx->img_epoch.assign(n_img, 0);
+  ctx->epoch = 0;
+  ctx->next_stage = 0;
   int64_t rows = 0;
   for (int i = 0; i < n_img; ++i) {
     ctx->img_row0[i] = static_cast<int32_t>(rows);
@@ -412,10 +453,16 @@ static void mark_image(sfm_ctx* ctx, int i) {
 // Host rows of images [first, first + n) -> staging -> pack kernels, queued on `up`.
 // desc[k] belongs to image first + k.  src == nullptr rows (commit) are taken from the bank.
 static int pack_images(sfm_ctx* ctx, int first, int n, const void* const* desc, bool f32,
-                       cudaStream_t up, bool record_events) {
+                       cudaStream_t up, bool record_events, int stage = 0) {
   const size_t elt = f32 ? 4 : 1;
   int32_t max_n = 0;
-  for (int k = 0; k < n; ++k) max_n = std::max(max_n, ctx->img_n[first + k]);
+  if (record_events) {
+    // asynchronous calls size the staging area for the whole layout at once: growing it later
+    // would cudaFree (a device-wide synchronisation) while the stream waits for a peer's flag
+    for (int32_t v : ctx->img_n) max_n = std::max(max_n, v);
+  } else {
+    for (int k = 0; k < n; ++k) max_n = std::max(max_n, ctx->img_n[first + k]);
+  }
   const size_t img_bytes = (static_cast<size_t>(max_n) * kDim * elt + 255) / 256 * 256;
   if (desc) CK(ctx->stage.ensure(2 * img_bytes + 512));
   for (int k = 0; k < n; ++k) {
@@ -435,7 +482,12 @@ static int pack_images(sfm_ctx* ctx, int first, int n, const void* const* desc, 
                         ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                         ctx->flags.as<uint32_t>(), up));
     ctx->launches += 3;
-    if (record_events) CK(cudaEventRecord(ctx->img_ev[i], up));      // image i is resident after this
+    if (record_events) {
+      CK(cudaEventRecord(ctx->img_ev[i], up));                        // image i is resident after this
+      ctx->img_evid[i] = i;
+      ctx->img_epoch[i] = ++ctx->epoch;
+      ctx->img_stage[i] = stage;
+    }
   }
   return SFM_OK;
 }
@@ -451,6 +503,25 @@ static int finish_pack(sfm_ctx* ctx, int first, int n, cudaStream_t up) {
   return SFM_OK;
 }
 
+static int ensure_image_events(sfm_ctx* ctx, int n_img) {
+  while (ctx->img_ev.size() < static_cast<size_t>(n_img)) {
+    cudaEvent_t e = nullptr;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->img_ev.push_back(e);
+  }
+  return SFM_OK;
+}
+
+// End of an asynchronous range call: the validation flags travel to the host behind everything
+// queued so far; the next sfm_match_pairs* call waits for them (finish_upload).
+static int queue_upload_verdict(sfm_ctx* ctx, int first, int n) {
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->upload_done, ctx->copy_stream));
+  ctx->upload_pending = true;
+  for (int k = 0; k < n; ++k) mark_image(ctx, first + k);
+  return SFM_OK;
+}
+
 static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const int32_t* n_desc,
                          int dim, bool f32, bool async) {
   if (!ctx) return SFM_E_INVALID;
@@ -462,22 +533,15 @@ static int upload_common(sfm_ctx* ctx, int n_img, const void* const* desc, const
   int rc = bank_layout(ctx, n_img, n_desc, dim, up);
   if (rc) return rc;
   if (async) {
-    while (ctx->img_ev.size() < static_cast<size_t>(n_img)) {
-      cudaEvent_t e = nullptr;
-      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      ctx->img_ev.push_back(e);
-    }
+    rc = ensure_image_events(ctx, n_img);
+    if (rc) return rc;
   }
   rc = pack_images(ctx, 0, n_img, desc, f32, up, async);
   if (rc) return rc;
   if (async) {
     // return at once: sfm_match_pairs makes its kernels wait for the images they read and
     // reports the validation result of this upload
-    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags.p, 4, cudaMemcpyDeviceToHost, up));
-    CK(cudaEventRecord(ctx->upload_done, up));
-    ctx->upload_pending = true;
-    for (int i = 0; i < n_img; ++i) mark_image(ctx, i);
-    return SFM_OK;
+    return queue_upload_verdict(ctx, 0, n_img);
   }
   return finish_pack(ctx, 0, n_img, up);
 }
@@ -529,6 +593,293 @@ int sfm_bank_commit(sfm_ctx* ctx, int first_img, int n_img) {
                         ctx->gmin8.as<int32_t>(), ctx->flags.as<uint32_t>(), ctx->stream));
   ctx->launches += 2;
   return finish_pack(ctx, first_img, n_img, ctx->stream);
+}
+
+// ---- staged arrival: the same three steps queued on the context's upload stream, no host
+// synchronisation.  A caller (one process per GPU) interleaves them with its own transfers on
+// that stream (sfm_upload_stream: NCCL all-gather of a region, cudaMemcpyPeerAsync):
+//   layout_async; upload_range_async(my part of region 0); <all-gather region 0>;
+//   commit_async(the peers' parts of region 0); upload_range_async(my part of region 1); ...
+// and then calls sfm_match_pairs once: pairs are visited in the order their images arrive
+// (every asynchronous range call is one arrival stage), each kernel launch waits only for the
+// images it reads, so matching overlaps the upload and exchange of the later regions.
+void* sfm_upload_stream(sfm_ctx* ctx) { return ctx ? static_cast<void*>(ctx->copy_stream) : nullptr; }
+
+int sfm_bank_layout_async(sfm_ctx* ctx, int n_img, const int32_t* n_desc, int dim) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = bank_layout(ctx, n_img, n_desc, dim, ctx->copy_stream);
+  if (rc) return rc;
+  return ensure_image_events(ctx, n_img);
+}
+
+int sfm_bank_upload_range_async(sfm_ctx* ctx, int first_img, int n_img, const void* const* desc,
+                                int elem_bytes) {
+  if (!ctx) return SFM_E_INVALID;
+  if (elem_bytes != 4 && elem_bytes != 1)
+    return fail(ctx, SFM_E_INVALID, "elem_bytes must be 4 (CV_32F) or 1 (CV_8U)");
+  int rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (n_img == 0) return SFM_OK;
+  if (!desc) return fail(ctx, SFM_E_INVALID, "null descriptor list");
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_image_events(ctx, static_cast<int>(ctx->img_n.size()));
+  if (rc) return rc;
+  rc = pack_images(ctx, first_img, n_img, desc, elem_bytes == 4, ctx->copy_stream, true, ctx->next_stage++);
+  if (rc) return rc;
+  return queue_upload_verdict(ctx, first_img, n_img);
+}
+
+static int commit_async(sfm_ctx* ctx, int first_img, int n_img) {
+  int rc = ensure_image_events(ctx, static_cast<int>(ctx->img_n.size()));
+  if (rc) return rc;
+  const int last = first_img + n_img - 1;
+  const int n_all = static_cast<int>(ctx->img_n.size());
+  const int row_begin = ctx->img_row0[first_img];
+  const int row_end = ctx->img_row0[last] + (ctx->img_n[last] + kRowPad - 1) / kRowPad * kRowPad;
+  CK(launch_commit_rows(ctx->desc.as<uint8_t>(), ctx->img_tab.as<int32_t>(), ctx->img_tab.as<int32_t>() + n_all,
+                        first_img, n_img, row_begin, row_end, ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(),
+                        ctx->gmin8.as<int32_t>(), ctx->flags.as<uint32_t>(), ctx->copy_stream));
+  ctx->launches += 2;
+  // one event for the whole range: its images become resident together
+  CK(cudaEventRecord(ctx->img_ev[last], ctx->copy_stream));
+  ++ctx->epoch;
+  for (int i = first_img; i <= last; ++i) {
+    ctx->img_evid[i] = last;
+    ctx->img_epoch[i] = ctx->epoch;
+    ctx->img_stage[i] = ctx->next_stage;
+  }
+  ++ctx->next_stage;
+  return queue_upload_verdict(ctx, first_img, n_img);
+}
+
+int sfm_bank_commit_async(sfm_ctx* ctx, int first_img, int n_img) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (n_img == 0) return SFM_OK;
+  CK(cudaSetDevice(ctx->device));
+  return commit_async(ctx, first_img, n_img);
+}
+
+// ---- peer exchange: push over NVLink with the copy engines, flags instead of a collective ----
+// Why not an NCCL all-gather: its kernels need SMs, and the persistent kNN kernel owns every SM
+// for the length of a launch, so the exchange of region k+1 would queue behind the matching of
+// region k.  Copy-engine pushes and stream memory operations run beside it.
+//   mailbox (device, per context): uint32 [1 + kPeerSlots][kPeerMaxRanks]
+//     row 0      READY[r]    = tag : rank r's bank is laid out for step `tag` and may be written
+//     row 1 + s  DATA[s][r]  = tag : rank r's push of slot s (a region of the image list) landed
+//   tags grow by one per step (wrap-safe >= compare), so nothing is ever reset.
+namespace {
+
+__global__ void flag_write_kernel(volatile uint32_t* p, uint32_t v) {
+  __threadfence_system();
+  *p = v;
+}
+__global__ void flag_wait_kernel(const volatile uint32_t* p, uint32_t v) {
+  while (static_cast<int32_t>(*p - v) < 0) __nanosleep(200);
+  __threadfence_system();
+}
+
+int flag_write(sfm_ctx* ctx, uint32_t* addr, uint32_t v) {
+  if (ctx->peer_memops) {
+    const CUresult r = ctx->stream_write(ctx->copy_stream, reinterpret_cast<CUdeviceptr>(addr), v, 0);
+    if (r != CUDA_SUCCESS) return fail(ctx, SFM_E_CUDA, "cuStreamWriteValue32 failed (try SFM_PEER_FLAGS=kernel)");
+  } else {
+    flag_write_kernel<<<1, 1, 0, ctx->copy_stream>>>(addr, v);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return SFM_OK;
+}
+
+int flag_wait(sfm_ctx* ctx, uint32_t* addr, uint32_t v) {
+  if (ctx->peer_memops) {
+    const CUresult r = ctx->stream_wait(ctx->copy_stream, reinterpret_cast<CUdeviceptr>(addr), v,
+                                        CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return fail(ctx, SFM_E_CUDA, "cuStreamWaitValue32 failed (try SFM_PEER_FLAGS=kernel)");
+  } else {
+    flag_wait_kernel<<<1, 1, 0, ctx->copy_stream>>>(addr, v);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  return SFM_OK;
+}
+
+int peer_ok(sfm_ctx* ctx) {
+  if (ctx->peer_n <= 0) return fail(ctx, SFM_E_INVALID, "no peers connected (sfm_peer_connect)");
+  if (ctx->desc.p != ctx->peer_bank_exported)
+    return fail(ctx, SFM_E_INVALID, "the bank was re-allocated after sfm_peer_export: export and connect again");
+  return SFM_OK;
+}
+
+struct PeerHandle {            // what sfm_peer_export writes (SFM_PEER_HANDLE_BYTES = 160)
+  cudaIpcMemHandle_t bank, mail;
+  uint64_t bank_bytes;
+  uint64_t pid;                // same process: the pointers below are used directly
+  uint64_t bank_ptr, mail_ptr;
+};
+static_assert(sizeof(PeerHandle) <= SFM_PEER_HANDLE_BYTES, "peer handle size");
+
+}  // namespace
+
+int sfm_peer_export(sfm_ctx* ctx, void* handle) {
+  if (!ctx || !handle) return SFM_E_INVALID;
+  if (ctx->img_n.empty() || ctx->bank_binary || !ctx->desc.p)
+    return fail(ctx, SFM_E_NOT_UPLOADED, "call sfm_bank_layout first");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->mailbox.p) {
+    CK(ctx->mailbox.ensure(4 * (1 + kPeerSlots) * kPeerMaxRanks));
+    CK(cudaMemset(ctx->mailbox.p, 0, 4 * (1 + kPeerSlots) * kPeerMaxRanks));
+  }
+  PeerHandle h;
+  memset(&h, 0, sizeof h);
+  CK(cudaIpcGetMemHandle(&h.bank, ctx->desc.p));
+  CK(cudaIpcGetMemHandle(&h.mail, ctx->mailbox.p));
+  h.bank_bytes = ctx->desc.cap;
+  h.pid = static_cast<uint64_t>(getpid());
+  h.bank_ptr = reinterpret_cast<uint64_t>(ctx->desc.p);
+  h.mail_ptr = reinterpret_cast<uint64_t>(ctx->mailbox.p);
+  memset(handle, 0, SFM_PEER_HANDLE_BYTES);
+  memcpy(handle, &h, sizeof h);
+  ctx->peer_bank_exported = ctx->desc.p;
+  return SFM_OK;
+}
+
+int sfm_peer_disconnect(sfm_ctx* ctx) {
+  if (!ctx) return SFM_E_INVALID;
+  if (ctx->peer_n > 0) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int r = 0; r < ctx->peer_n; ++r) {
+      if (r == ctx->peer_rank || !ctx->peer_ipc[r]) continue;
+      if (ctx->peer_bank[r]) cudaIpcCloseMemHandle(ctx->peer_bank[r]);
+      if (ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
+    }
+  }
+  ctx->peer_bank.clear();
+  ctx->peer_mail.clear();
+  ctx->peer_ipc.clear();
+  ctx->peer_n = 0;
+  ctx->peer_rank = -1;
+  return SFM_OK;
+}
+
+int sfm_peer_connect(sfm_ctx* ctx, int my_rank, int n_ranks, const void* handles) {
+  if (!ctx || !handles) return SFM_E_INVALID;
+  if (n_ranks < 1 || n_ranks > kPeerMaxRanks || my_rank < 0 || my_rank >= n_ranks)
+    return fail(ctx, SFM_E_INVALID, "rank / world size out of range (at most 64 ranks)");
+  if (!ctx->mailbox.p || !ctx->peer_bank_exported)
+    return fail(ctx, SFM_E_INVALID, "call sfm_peer_export on this context first");
+  sfm_peer_disconnect(ctx);
+  CK(cudaSetDevice(ctx->device));
+  ctx->peer_bank.assign(n_ranks, nullptr);
+  ctx->peer_mail.assign(n_ranks, nullptr);
+  ctx->peer_ipc.assign(n_ranks, 0);
+  ctx->peer_rank = my_rank;
+  ctx->peer_n = n_ranks;
+  const uint64_t pid = static_cast<uint64_t>(getpid());
+  for (int r = 0; r < n_ranks; ++r) {
+    PeerHandle h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + static_cast<size_t>(r) * SFM_PEER_HANDLE_BYTES, sizeof h);
+    if (r == my_rank) continue;
+    if (h.bank_bytes < static_cast<uint64_t>(ctx->bank_rows) * kDim) {
+      sfm_peer_disconnect(ctx);
+      return fail(ctx, SFM_E_INVALID, "a peer's bank is smaller than this layout: same sfm_bank_layout on every rank");
+    }
+    if (h.pid == pid) {                   // several contexts of one process: plain device pointers
+      ctx->peer_bank[r] = reinterpret_cast<uint8_t*>(h.bank_ptr);
+      ctx->peer_mail[r] = reinterpret_cast<uint32_t*>(h.mail_ptr);
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, ctx->peer_bank[r]) == cudaSuccess && at.device == ctx->device) {
+        // two contexts of one process on ONE device share the device's hardware queues: a stream
+        // that waits for a flag can sit in front of the very stream that has to raise it
+        sfm_peer_disconnect(ctx);
+        return fail(ctx, SFM_E_INVALID, "peers of one process must be on different devices (or use one process per rank)");
+      }
+      if (cudaPointerGetAttributes(&at, ctx->peer_bank[r]) == cudaSuccess && at.device != ctx->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          sfm_peer_disconnect(ctx);
+          return fail(ctx, SFM_E_CUDA, "cudaDeviceEnablePeerAccess failed");
+        }
+        cudaGetLastError();
+      }
+    } else {
+      void *pb = nullptr, *pm = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&pb, h.bank, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pm, h.mail, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        if (pb) cudaIpcCloseMemHandle(pb);
+        cudaGetLastError();
+        sfm_peer_disconnect(ctx);
+        ctx->err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e);
+        return SFM_E_CUDA;
+      }
+      ctx->peer_bank[r] = static_cast<uint8_t*>(pb);
+      ctx->peer_mail[r] = static_cast<uint32_t*>(pm);
+      ctx->peer_ipc[r] = 1;
+    }
+  }
+  return SFM_OK;
+}
+
+int sfm_bank_ready_async(sfm_ctx* ctx, uint32_t tag) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = peer_ok(ctx);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->peer_n; ++r) {
+    if (r == ctx->peer_rank) continue;
+    rc = flag_write(ctx, ctx->peer_mail[r] + ctx->peer_rank, tag);      // READY[me] in r's mailbox
+    if (rc) return rc;
+  }
+  return SFM_OK;
+}
+
+int sfm_bank_push_range_async(sfm_ctx* ctx, int first_img, int n_img, int slot, uint32_t tag) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = peer_ok(ctx);
+  if (rc) return rc;
+  rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kPeerSlots) return fail(ctx, SFM_E_INVALID, "slot must be 0..14");
+  CK(cudaSetDevice(ctx->device));
+  size_t off = 0, end = 0;
+  if (n_img > 0) {
+    const int last = first_img + n_img - 1;
+    off = static_cast<size_t>(ctx->img_row0[first_img]) * kDim;
+    end = (static_cast<size_t>(ctx->img_row0[last]) +
+           (static_cast<size_t>(ctx->img_n[last]) + kRowPad - 1) / kRowPad * kRowPad) * kDim;
+  }
+  uint32_t* mine = ctx->mailbox.as<uint32_t>();
+  // start with the right-hand neighbour so that the ranks do not all write to rank 0 first
+  for (int k = 1; k < ctx->peer_n; ++k) {
+    const int r = (ctx->peer_rank + k) % ctx->peer_n;
+    rc = flag_wait(ctx, mine + r, tag);                                  // r's bank is laid out
+    if (rc) return rc;
+    if (end > off)
+      CK(cudaMemcpyAsync(ctx->peer_bank[r] + off, ctx->desc.as<uint8_t>() + off, end - off,
+                         cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    rc = flag_write(ctx, ctx->peer_mail[r] + (1 + slot) * kPeerMaxRanks + ctx->peer_rank, tag);
+    if (rc) return rc;
+  }
+  return SFM_OK;
+}
+
+int sfm_bank_pull_commit_async(sfm_ctx* ctx, int src_rank, int first_img, int n_img, int slot, uint32_t tag) {
+  if (!ctx) return SFM_E_INVALID;
+  int rc = peer_ok(ctx);
+  if (rc) return rc;
+  rc = range_ok(ctx, first_img, n_img);
+  if (rc) return rc;
+  if (slot < 0 || slot >= kPeerSlots) return fail(ctx, SFM_E_INVALID, "slot must be 0..14");
+  if (src_rank < 0 || src_rank >= ctx->peer_n || src_rank == ctx->peer_rank)
+    return fail(ctx, SFM_E_INVALID, "src_rank must name a peer");
+  CK(cudaSetDevice(ctx->device));
+  rc = flag_wait(ctx, ctx->mailbox.as<uint32_t>() + (1 + slot) * kPeerMaxRanks + src_rank, tag);
+  if (rc) return rc;
+  if (n_img == 0) return SFM_OK;
+  return commit_async(ctx, first_img, n_img);
 }
 
 int sfm_bank_image_rows(const sfm_ctx* ctx, int img, int64_t* row0, int64_t* rows) {
@@ -698,26 +1049,56 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     const int B = static_cast<int>(std::max<size_t>(1, ctx->l2_bytes * 6 / 10 / (2 * img_bytes)));
     std::vector<int32_t>& order = ctx->h_order;
     order.resize(n_pairs);
-    for (int p = 0; p < n_pairs; ++p) order[p] = p;
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-      const int qa = pair_q[a] / B, qb = pair_q[b] / B, ta = pair_t[a] / B, tb = pair_t[b] / B;
-      if (ta != tb) return ta < tb;      // train block outermost: an asynchronous upload is
-      if (qa != qb) return qa < qb;      // consumed in image order (block (qb, tb) needs images < (tb+1) B)
-      if (pair_q[a] != pair_q[b]) return pair_q[a] < pair_q[b];
-      if (pair_t[a] != pair_t[b]) return pair_t[a] < pair_t[b];
-      return a < b;
-    });
+    // arrival stage of a pair = the later of its two images' stages (0 unless a staged
+    // asynchronous upload is pending): pairs whose images are there first are visited first
+    const bool staged = ctx->upload_pending && ctx->next_stage > 1;
+    auto stage_of = [&](int32_t p) {
+      return staged ? std::max(ctx->img_stage[pair_q[p]], ctx->img_stage[pair_t[p]]) : 0;
+    };
+    // Block key (stage, train block, query block): train block outermost, so that an asynchronous
+    // upload is consumed in image order (block (qb, tb) needs images < (tb + 1) B).  Pairs keep
+    // their caller order inside a block.  This runs on the host in front of the first launch of
+    // every call: a stable counting sort over the (few) block keys, O(n_pairs), instead of a
+    // comparison sort (2.6 ms for 19 900 pairs).
+    const int64_t nb = (n_img + B - 1) / B;
+    const int64_t n_keys = static_cast<int64_t>(staged ? ctx->next_stage : 1) * nb * nb;
+    auto key_of = [&](int32_t p) {
+      return (static_cast<int64_t>(stage_of(p)) * nb + pair_t[p] / B) * nb + pair_q[p] / B;
+    };
+    if (n_keys <= 4ll * n_pairs + 1024) {
+      std::vector<int32_t>& head = ctx->h_bucket;
+      std::vector<int32_t>& keys = ctx->h_key;
+      head.assign(static_cast<size_t>(n_keys) + 1, 0);
+      keys.resize(n_pairs);
+      for (int p = 0; p < n_pairs; ++p) {
+        keys[p] = static_cast<int32_t>(key_of(p));
+        ++head[keys[p] + 1];
+      }
+      for (int64_t k = 0; k < n_keys; ++k) head[k + 1] += head[k];
+      for (int p = 0; p < n_pairs; ++p) order[head[keys[p]]++] = p;
+    } else {                                   // huge image lists: sort (key, pair) words
+      std::vector<std::pair<int64_t, int32_t>> kp(n_pairs);
+      for (int p = 0; p < n_pairs; ++p) kp[p] = std::make_pair(key_of(p), p);
+      std::sort(kp.begin(), kp.end());
+      for (int p = 0; p < n_pairs; ++p) order[p] = kp[p].second;
+    }
     const int qblock = ctx->bank_binary ? 128 : kTileM;   // query rows per work item
     ctx->h_groups.clear();                                // (first item, last image needed) per block
-    int cur_q = -1, cur_t = -1;
+    int cur_q = -1, cur_t = -1, cur_s = -1;
     for (int32_t p : order) {
-      const int qb = pair_q[p] / B, tb = pair_t[p] / B;
-      if (qb != cur_q || tb != cur_t) {
-        ctx->h_groups.push_back(std::make_pair(n_items, 0));
+      const int qb = pair_q[p] / B, tb = pair_t[p] / B, st = stage_of(p);
+      if (qb != cur_q || tb != cur_t || st != cur_s) {
+        ctx->h_groups.push_back(std::make_pair(n_items, pair_q[p]));
         cur_q = qb;
         cur_t = tb;
+        cur_s = st;
       }
-      ctx->h_groups.back().second = std::max(ctx->h_groups.back().second, std::max(pair_q[p], pair_t[p]));
+      // the block waits for the image whose arrival event was recorded last
+      if (ctx->upload_pending) {
+        int& latest = ctx->h_groups.back().second;
+        if (ctx->img_epoch[pair_q[p]] > ctx->img_epoch[latest]) latest = pair_q[p];
+        if (ctx->img_epoch[pair_t[p]] > ctx->img_epoch[latest]) latest = pair_t[p];
+      }
       ordoff.push_back(make_int2(p, static_cast<int>(n_items)));
       n_items += (pairs[p].nq + qblock - 1) / qblock;
       if (n_items > INT32_MAX) return fail(ctx, SFM_E_INVALID, "too many query blocks");
@@ -757,13 +1138,24 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     if (n_items > 0) ctx->launches += 2;
   } else {
     if (ctx->upload_pending) {
-      // one launch per L2 block, each waiting only for the last image it reads: matching
-      // starts while later images are still crossing PCIe
-      for (size_t g = 0; g < ctx->h_groups.size(); ++g) {
+      // launches follow the arrival of the images: a new launch starts where an L2 block needs an
+      // image that arrives later than everything waited for so far (every launch of the persistent
+      // kernel ends with a tail of idle SMs, so blocks that need nothing new share a launch);
+      // matching starts while later images are still crossing PCIe / NVLink
+      int64_t waited = -1;                       // latest arrival epoch this stream waits for
+      size_t g = 0;
+      while (g < ctx->h_groups.size()) {
         const int64_t first = ctx->h_groups[g].first;
-        const int64_t last = g + 1 < ctx->h_groups.size() ? ctx->h_groups[g + 1].first : n_items;
+        const int img = ctx->h_groups[g].second;
+        if (ctx->img_epoch[img] > waited) {
+          CK(cudaStreamWaitEvent(ctx->stream, ctx->img_ev[ctx->img_evid[img]], 0));
+          waited = ctx->img_epoch[img];
+        }
+        size_t e = g + 1;
+        while (e < ctx->h_groups.size() && ctx->img_epoch[ctx->h_groups[e].second] <= waited) ++e;
+        const int64_t last = e < ctx->h_groups.size() ? ctx->h_groups[e].first : n_items;
+        g = e;
         if (last <= first) continue;
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->img_ev[ctx->h_groups[g].second], 0));
         CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                        ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>() + first,
                        static_cast<int>(last - first), ctx->knn.as<Knn2>(), ctx->n_sms,

@@ -110,7 +110,7 @@ constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-
 #ifndef SFM_COLD_WINDOWS
 #define SFM_COLD_WINDOWS 1                      // windows at the start of a sweep that skip the filter
 #endif
-constexpr int kPreVoteTiles = 128;              // sweeps of >= 16384 train rows use the chunk pre-vote
+constexpr int kPreVoteTiles = 128;              // exact search: sweeps of >= 16384 train rows use the chunk pre-vote
 constexpr int kHalfM = kTileM / 2;              // 128 rows per MMA
 constexpr int kCkSlots = 16;                    // ring of per-tile column keys (512 B each)
 
@@ -235,10 +235,15 @@ __device__ __forceinline__ int group_max(const uint32_t* r) {
 //            neg2 = -2 in a register ptxas cannot see through, so that the multiply-add stays
 //            an IMAD on the FMA pipe instead of an IADD3 on the (limiting) ALU pipe.
 //   kPreVote : one vote for the whole piece in front of the per-group votes.  A vote costs
-//            about two ALU instructions; in long sweeps (rare hits) most pieces need only that
-//            one, in 8192-column sweeps 54 % of the 32-column pieces contain a hit and it does
-//            not pay (measured: -2.6 % there, +7 % on a 65536-column train image), so the kernel
-//            picks per work item.
+//            about two ALU instructions; when few pieces contain a hit most of them need only
+//            that one.  Exact search: 54 % of the 32-column pieces of an 8192-column sweep
+//            contain a hit and it does not pay (measured: -2.6 % there, +7 % on a 65536-column
+//            train image), so the kernel picks per work item.  Match-only search (35 % of the
+//            pieces hit): always (+2.5 % on the 8192-column workload).  A variant that tests
+//            the piece's maximum against a precomputed 32-column minimum norm first and loads /
+//            tests the groups only on a hit has 6 instructions fewer per quiet piece but is
+//            slower (2240 vs 2292 TOP/s): the group tests then sit serially behind the vote
+//            instead of running alongside the max trees.
 // `mid` runs once inside the update, after the filter votes and before the inserts (the sweep
 // hands the TMEM buffer back there).
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
@@ -629,7 +634,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         const int cold = min(kCold, ntiles);
         auto sweeps = [&](auto bg_tag) {
           if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, bg_tag, 0, cold);
-          if (ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, bg_tag, cold, ntiles);
+          if (kMatchOnly || ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, bg_tag, cold, ntiles);
           else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, bg_tag, cold, ntiles);
         };
         if constexpr (kParts == 2) {

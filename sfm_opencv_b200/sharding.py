@@ -70,6 +70,73 @@ def shard_query_rows(n_query: int, world_size: int, block: int = 256):
     return out
 
 
+def staged_image_ranges(n_img: int, world_size: int, n_stages: int):
+    """Bank order for the staged (overlapped) multi-GPU upload: the image list is cut into
+    `n_stages` REGIONS; region k holds one contiguous part of every rank, rank-major, so that one
+    in-place all-gather moves a whole region.  Rank r uploads regions[k][r] = (first_img, count)
+    for every k -- still 1/N of the images per rank, each image crosses PCIe once.  With n_img a
+    multiple of world_size the parts of a region are equal (what ncclAllGather needs)."""
+    if world_size <= 0 or n_stages <= 0:
+        raise ValueError("world_size and n_stages must be positive")
+    per_rank = [e - s for s, e in shard_range(n_img, world_size)]
+    parts = [[e - s for s, e in shard_range(c, n_stages)] for c in per_rank]    # [rank][stage]
+    regions, first = [], 0
+    for k in range(n_stages):
+        row = []
+        for r in range(world_size):
+            row.append((first, parts[r][k]))
+            first += parts[r][k]
+        regions.append(row)
+    return regions
+
+
+def image_regions(n_img: int, regions) -> np.ndarray:
+    """Region index of every image of a staged_image_ranges layout."""
+    out = np.zeros(n_img, np.int32)
+    for k, row in enumerate(regions):
+        for first, count in row:
+            out[first:first + count] = k
+    return out
+
+
+def shard_pairs_staged(pairs, n_desc, world_size: int, img_region):
+    """Pair shards for the staged upload: a pair can be matched once the later of its two images'
+    regions has arrived (its stage); the pairs of every stage are split into `world_size`
+    contiguous cost-balanced blocks, and rank r takes block r of every stage, earliest stage first.
+    Every rank therefore has work as soon as region 0 is there.  Returns one int64 index array
+    (into `pairs`) per rank; the arrays partition the pair list."""
+    p = np.asarray(pairs, np.int64).reshape(-1, 2)
+    reg = np.asarray(img_region, np.int64)
+    stage = np.maximum(reg[p[:, 0]], reg[p[:, 1]]) if len(p) else np.zeros(0, np.int64)
+    out = [[] for _ in range(world_size)]
+    for s in np.unique(stage):
+        idx = np.nonzero(stage == s)[0]
+        for r, (lo, hi) in enumerate(shard_pairs(p[idx], n_desc, world_size)):
+            out[r].append(idx[lo:hi])
+    return [np.concatenate(o) if o else np.zeros(0, np.int64) for o in out]
+
+
+def gather_match_lists_indexed(local_matches, pair_index, n_pairs: int, group=None):
+    """gather_match_lists for shards that are index lists (shard_pairs_staged) instead of ranges:
+    local_matches[k] belongs to pair pair_index[k]; the result is in pair order."""
+    import torch.distributed as dist
+    idx = [int(i) for i in pair_index]
+    payload = (idx, [np.asarray(m) for m in local_matches])
+    if not dist.is_available() or not dist.is_initialized():
+        gathered = [payload]
+    else:
+        gathered = [None] * dist.get_world_size(group)
+        dist.all_gather_object(gathered, payload, group=group)
+    out = [None] * n_pairs
+    for ids, ms in gathered:
+        assert len(ids) == len(ms)
+        for i, m in zip(ids, ms):
+            assert out[i] is None, "pair matched by two ranks"
+            out[i] = m
+    assert all(m is not None for m in out), "pair shards do not cover the pair list"
+    return out
+
+
 def gather_match_lists(local_matches, start: int, stop: int, n_pairs: int, group=None):
     """Final host gather (the only exchange on the path): every rank contributes the match
     arrays of its pair range; rank order == pair order, so the result is the reference's

@@ -494,3 +494,122 @@ def test_two_devices_in_one_process():
         got0 = _match_bytes(c0, pairs[s0:e0])
         got1 = _match_bytes(c1, pairs[s1:e1])
         assert tuple(x + y for x, y in zip(got0, got1)) == want
+
+
+def _staged_arrival(c, whole, sizes, bank, regions, rank, bad=None):
+    """Drives context `c` as rank `rank` of the staged multi-GPU upload on ONE device: its own parts
+    come from the host (asynchronously), the peers' parts are copied on the upload stream from the
+    bank of `whole` (a context that holds everything) -- the place an NCCL all-gather takes in
+    bench.py.  Nothing synchronises with the host before match_pairs."""
+    import torch
+    c.bank_layout(sizes, overlap=True)
+    dst, src = c.bank_as_torch(), whole.bank_as_torch()
+    up = c.upload_stream_torch()
+    for row in regions:
+        first, count = row[rank]
+        part = [bank[i].astype(np.float32) for i in range(first, first + count)]
+        if bad is not None and first <= bad < first + count:
+            part[bad - first][0, 0] = 300.0
+        c.bank_upload_range(first, part, overlap=True)
+        r_first, r_end = row[0][0], row[-1][0] + row[-1][1]
+        with torch.cuda.stream(up):
+            for a, b in ((r_first, first), (first + count, r_end)):
+                if b > a:
+                    r0, _ = c.bank_image_rows(a)
+                    rl, nl = c.bank_image_rows(b - 1)
+                    dst[r0:rl + nl].copy_(src[r0:rl + nl], non_blocking=True)
+        c.bank_commit(r_first, first - r_first, overlap=True)
+        c.bank_commit(first + count, r_end - first - count, overlap=True)
+
+
+def test_staged_arrival_equals_whole_upload(ctx):
+    """sfm_bank_layout_async / _upload_range_async / _commit_async: images arrive in stages on the
+    upload stream, one sfm_match_pairs call matches the pairs in arrival order.  Match lists, min_dist
+    and kNN rows equal the plain upload bit for bit, for both ranks of a 2-rank layout."""
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200.sharding import image_regions, shard_pairs_staged, staged_image_ranges
+    pytest.importorskip("torch")
+    sizes = [700, 300, 513, 256, 300, 1100, 2, 900, 650, 1500]
+    bank = [synth.sift_like(n, 140 + k) for k, n in enumerate(sizes)]
+    bank[3][:100] = bank[0][:100]
+    bank[8][:200] = bank[1][:200]
+    pairs = M.all_pairs(len(bank))
+    ctx.upload_descriptors(bank)
+    regions = staged_image_ranges(len(bank), 2, 3)
+    shards = shard_pairs_staged(pairs, sizes, 2, image_regions(len(bank), regions))
+    for rank in range(2):
+        mine = [pairs[i] for i in shards[rank]]
+        want = _match_bytes(ctx, mine)
+        with sfm.Context(0) as c:
+            for _ in range(2):                                 # a second step re-uses the layout
+                _staged_arrival(c, ctx, sizes, bank, regions, rank)
+                assert _match_bytes(c, mine) == want
+
+
+def test_staged_arrival_reports_bad_descriptors(ctx):
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    from sfm_opencv_b200.sharding import staged_image_ranges
+    pytest.importorskip("torch")
+    sizes = [300, 300, 300, 300]
+    bank = [synth.sift_like(n, 150 + k) for k, n in enumerate(sizes)]
+    ctx.upload_descriptors(bank)
+    regions = staged_image_ranges(4, 2, 2)
+    with sfm.Context(0) as c:
+        _staged_arrival(c, ctx, sizes, bank, regions, 0, bad=regions[1][0][0])
+        with pytest.raises(sfm.SfmError) as e:
+            c.match_pairs(M.all_pairs(4))
+        assert e.value.code == _capi.SFM_E_RANGE
+        _staged_arrival(c, ctx, sizes, bank, regions, 0)       # the context recovers
+        c.match_pairs(M.all_pairs(4))
+
+
+@pytest.mark.parametrize("flags", ["memop", "kernel"])
+def test_peer_push_exchange_two_processes(flags, monkeypatch):
+    """sfm_peer_* / sfm_bank_push_range_async / _pull_commit_async between two PROCESSES (one per rank,
+    as bench.py --gpus N; here both on cuda:0 -- CUDA IPC peer memory, copy-engine pushes, mailbox
+    flags by stream memory operations or 1-thread kernels).  The workers run under a timeout: a
+    protocol error is a stream that waits for a flag forever, and that must fail this test, not hang
+    the suite."""
+    import multiprocessing as mp
+    import queue
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)                   # spawn hands sys.path to the children
+    import peer_push_worker as W
+    monkeypatch.setenv("SFM_PEER_FLAGS", flags)
+    mpc = mp.get_context("spawn")
+    q01, q10, result = mpc.Queue(), mpc.Queue(), mpc.Queue()
+    procs = [mpc.Process(target=W.run, args=(0, q10, q01, result)),
+             mpc.Process(target=W.run, args=(1, q01, q10, result))]
+    for p in procs:
+        p.start()
+    got = {}
+    try:
+        for _ in range(2):
+            rank, msg = result.get(timeout=150)
+            got[rank] = msg
+    except queue.Empty:
+        pass
+    finally:
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+    assert got == {0: "ok", 1: "ok"}, got
+
+
+def test_peer_connect_refuses_two_contexts_on_one_device(ctx):
+    """One process, one device: a stream waiting for a flag may sit in front of the stream that has
+    to raise it (shared hardware queues), so the library refuses the connection."""
+    import sfm_opencv_b200 as sfm
+    from sfm_opencv_b200 import _capi
+    with sfm.Context(0) as a, sfm.Context(0) as b:
+        for c in (a, b):
+            c.bank_layout([300, 300])
+        handles = [a.peer_export(), b.peer_export()]
+        with pytest.raises(sfm.SfmError) as e:
+            a.peer_connect(0, handles)
+        assert e.value.code == _capi.SFM_E_INVALID

@@ -189,3 +189,73 @@ def test_huber_cost_is_additive_over_observation_ranges():
     for world in (2, 3, 8):
         parts = [G.huber_cost(r[s:e], 4.0) for s, e in S.shard_range(len(r), world)]
         assert abs(sum(parts) - whole) <= 1e-12 * whole
+
+
+# ---- staged (overlapped) multi-GPU upload: image regions, per-stage pair shards, indexed gather
+@pytest.mark.parametrize("n_img,world,stages", [(200, 8, 3), (200, 2, 3), (10, 4, 3), (7, 2, 1), (5, 8, 2)])
+def test_staged_image_ranges_partition_the_images(n_img, world, stages):
+    regions = S.staged_image_ranges(n_img, world, stages)
+    assert len(regions) == stages and all(len(row) == world for row in regions)
+    flat = [rng for row in regions for rng in row]
+    nxt = 0
+    for first, count in flat:                                  # bank order: region-major, rank-major, contiguous
+        assert first == nxt and count >= 0
+        nxt += count
+    assert nxt == n_img
+    per_rank = [sum(regions[k][r][1] for k in range(stages)) for r in range(world)]
+    assert sorted(per_rank) == sorted(e - s for s, e in S.shard_range(n_img, world))   # still 1/N per rank
+    if n_img % world == 0:
+        assert all(len({c for _, c in row}) == 1 for row in regions)                   # equal parts: in-place all-gather
+    reg = S.image_regions(n_img, regions)
+    assert np.all(np.diff(reg) >= 0) and reg.max() <= stages - 1
+
+
+def test_shard_pairs_staged_partitions_and_balances_every_stage():
+    n_img, world, stages = 40, 4, 3
+    sizes = [1000 + 37 * (i % 5) for i in range(n_img)]
+    pairs = [(i, j) for i in range(n_img) for j in range(i + 1, n_img)]
+    reg = S.image_regions(n_img, S.staged_image_ranges(n_img, world, stages))
+    shards = S.shard_pairs_staged(pairs, sizes, world, reg)
+    allidx = np.concatenate(shards)
+    assert len(allidx) == len(pairs) and len(np.unique(allidx)) == len(pairs)
+    p = np.asarray(pairs)
+    stage = np.maximum(reg[p[:, 0]], reg[p[:, 1]])
+    cost = S.pair_cost(sizes, pairs)
+    for idx in shards:
+        assert np.all(np.diff(stage[idx]) >= 0)                # earliest stage first
+    for s in range(stages):
+        per_rank = [cost[idx[stage[idx] == s]].sum() for idx in shards]
+        assert max(per_rank) <= 1.1 * (sum(per_rank) / world) + cost.max()
+
+
+def _worker_indexed(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_img = 6
+    pairs = [(i, j) for i in range(n_img) for j in range(i + 1, n_img)]
+    reg = S.image_regions(n_img, S.staged_image_ranges(n_img, world, 2))
+    mine = S.shard_pairs_staged(pairs, [100] * n_img, world, reg)[rank]
+    local = [np.full(3, 100 * pairs[i][0] + pairs[i][1], np.int32) for i in mine]    # stands for a match list
+    full = S.gather_match_lists_indexed(local, mine, len(pairs))
+    if rank == 0:
+        q.put([int(x[0]) for x in full])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_indexed_gather_world2_gloo_is_in_pair_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_indexed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [100 * i + j for i in range(6) for j in range(i + 1, 6)]
