@@ -179,7 +179,7 @@ def workload_config(args, world):
                         f"5*max(min_dist,10) gate (BASELINE.json configs[2])",
             "pairs": n_pairs, "images": args.images, "desc_per_image": args.desc,
             "sharding": (f"contiguous pair blocks over {world} rank(s), no collective" if world == 1 else
-                         f"{world} ranks; per arrival stage of the staged upload ({max(1, args.stages)} image regions) "
+                         f"{world} ranks; per arrival stage of the staged upload (image regions {args.stage_weights or args.stages}) "
                          "contiguous cost-balanced pair blocks; no collective on results"),
             "l2": f"descriptor bank {args.images * args.desc * 128 / 1e6:.0f} MB "
                   f"{'>' if args.images * args.desc * 128 > 126e6 else '<='} 126 MB L2; "
@@ -482,7 +482,8 @@ def run_b200(args, rank, local_rank, world):
     else:
         # staged layout (see the e2e block below): image regions in arrival order, and pair shards
         # that give every rank its share of every arrival stage
-        regions = staged_image_ranges(args.images, world, max(1, args.stages))
+        sw = [float(x) for x in args.stage_weights.split(",")] if args.stage_weights else None
+        regions = staged_image_ranges(args.images, world, len(sw) if sw else max(1, args.stages), sw)
         mine_idx = shard_pairs_staged(pairs, n_desc, world, image_regions(args.images, regions))[rank]
         my_pairs = pairs_np[mine_idx]
     n_pairs = len(pairs)
@@ -867,6 +868,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N > 1: how the packed rows travel GPU to GPU (copy-engine pushes + flags, or NCCL all-gather)")
+    ap.add_argument("--stage-weights", default="1,2,3",
+                    help="N > 1: relative sizes of the regions, e.g. 1,2 (overrides --stages; '' = equal regions)")
     ap.add_argument("--stages", type=int, default=2,
                     help="N > 1: regions of the image list whose upload + NVLink exchange is pipelined with matching")
     args = ap.parse_args()

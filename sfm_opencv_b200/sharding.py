@@ -70,16 +70,35 @@ def shard_query_rows(n_query: int, world_size: int, block: int = 256):
     return out
 
 
-def staged_image_ranges(n_img: int, world_size: int, n_stages: int):
+def _split_weighted(n: int, weights):
+    """n items in len(weights) consecutive parts proportional to the weights (largest remainders)."""
+    w = np.asarray(weights, np.float64)
+    if len(w) == 0 or (w <= 0).any():
+        raise ValueError("weights must be positive")
+    ideal = n * w / w.sum()
+    parts = np.floor(ideal).astype(np.int64)
+    for k in np.argsort(-(ideal - parts), kind="stable")[: n - int(parts.sum())]:
+        parts[k] += 1
+    return [int(x) for x in parts]
+
+
+def staged_image_ranges(n_img: int, world_size: int, n_stages: int, weights=None):
     """Bank order for the staged (overlapped) multi-GPU upload: the image list is cut into
     `n_stages` REGIONS; region k holds one contiguous part of every rank, rank-major, so that one
     in-place all-gather moves a whole region.  Rank r uploads regions[k][r] = (first_img, count)
     for every k -- still 1/N of the images per rank, each image crosses PCIe once.  With n_img a
-    multiple of world_size the parts of a region are equal (what ncclAllGather needs)."""
+    multiple of world_size the parts of a region are equal (what ncclAllGather needs).
+    weights (one per stage, default equal): relative sizes of the regions.  A small first region
+    shortens the time before matching can start; matching its pairs then has to cover the arrival
+    of the next one (the work of the first k regions grows with the square of their share)."""
     if world_size <= 0 or n_stages <= 0:
         raise ValueError("world_size and n_stages must be positive")
+    if weights is None:
+        weights = [1.0] * n_stages
+    if len(weights) != n_stages:
+        raise ValueError("one weight per stage")
     per_rank = [e - s for s, e in shard_range(n_img, world_size)]
-    parts = [[e - s for s, e in shard_range(c, n_stages)] for c in per_rank]    # [rank][stage]
+    parts = [_split_weighted(c, weights) for c in per_rank]                    # [rank][stage]
     regions, first = [], 0
     for k in range(n_stages):
         row = []
