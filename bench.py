@@ -27,6 +27,8 @@ Other workloads (their own metric; lines kept under profiles/):
                            ranks, min_dist reduced across ranks (MIN) between pass 1 and pass 2
     --workload geometry    BASELINE config 5: 4M points x V views, DLT triangulation + reprojection
                            residuals, points / observations sharded over the ranks, Huber cost summed
+    --workload datasets    BASELINE configs 1-2: the bundled datasets (committed SIFT fixtures) in the
+                           reference's pair schedule, end to end vs the reference's CPU library call
 """
 from __future__ import annotations
 
@@ -850,6 +852,82 @@ def run_geometry(args, rank, local_rank, world):
     rk.close()
 
 
+def run_datasets(args, rank, local_rank, world):
+    """BASELINE configs 0-1 on the reference's bundled datasets (SIFT descriptors extracted once by
+    tests/golden/make_golden.py with the image's cv2 and committed as fixtures: /root/reference does
+    not exist on the GPU box).  Per dataset: the reference's own schedule -- consecutive pairs
+    (match_features_for_all, NViewReconstuct.cpp:850-871) -- through the host API (pinned CV_32F in,
+    DMatch lists out) against the reference's CPU library call on the same pairs, the match lists
+    compared with the committed golden lists; desktop / crazyhorse also as exhaustive all-pairs."""
+    if rank != 0:
+        return
+    import cv2
+    import sfm_opencv_b200 as sfm
+    from oracle import matching as M
+    ctx = sfm.Context(local_rank)
+    gdir = os.path.join(ROOT, "tests", "golden")
+    out, tot_pairs, tot_gpu, tot_cpu = {}, 0, 0.0, 0.0
+    for name in ("desktop", "crazyhorse", "dog"):
+        g = np.load(os.path.join(gdir, f"{name}_sift.npz"))
+        n = int(g["n_img"])
+        bank = [g[f"desc_{i}"] for i in range(n)]
+        host = []
+        for i, b in enumerate(bank):
+            h = ctx.pinned_empty(b.shape, np.float32, f"{name}{i}")
+            h[...] = b
+            host.append(h)
+        for sched in ("consecutive", "allpairs"):
+            if sched == "allpairs" and name == "dog":
+                continue                                        # 120 pairs of ~17k x 17k: too long for the CPU leg
+            pairs = M.consecutive_pairs(n) if sched == "consecutive" else M.all_pairs(n)
+            pa = np.asarray(pairs, np.int32)
+            for _ in range(2):
+                ctx.upload_descriptors(host, overlap=True)
+                ctx.match_pairs(pa, copy=False)
+            reps = max(3, args.steps)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ctx.upload_descriptors(host, overlap=True)
+                m, md, _ = ctx.match_pairs(pa, copy=False)
+            gpu_s = (time.perf_counter() - t0) / reps
+            t0 = time.perf_counter()
+            ref = []
+            for a, b in pairs:
+                dist, idx = M.knn2_cv(host[a], host[b])
+                ref.append(M.filter_matches(dist, idx))
+            cpu_s = time.perf_counter() - t0
+            same = all(np.array_equal(m[p]["queryIdx"], ref[p][0][:, 0]) and np.array_equal(m[p]["trainIdx"], ref[p][0][:, 1]) and
+                       np.array_equal(m[p]["distance"].view(np.uint32), ref[p][1].view(np.uint32)) and
+                       np.float32(md[p]).view(np.uint32) == np.float32(ref[p][2]).view(np.uint32) for p in range(len(pairs)))
+            golden_ok = None
+            if sched == "consecutive":
+                golden_ok = all(np.array_equal(m[p]["queryIdx"], g[f"match_{p}"][:, 0]) and
+                                np.array_equal(m[p]["trainIdx"], g[f"match_{p}"][:, 1]) for p in range(len(pairs)))
+            ops = 2.0 * 128 * sum(len(bank[a]) * len(bank[b]) for a, b in pairs)
+            out[f"{name}_{sched}"] = {
+                "images": n, "descriptors": [len(b) for b in bank], "pairs": len(pairs),
+                "matches": [int(len(m[p])) for p in range(len(pairs))][:16],
+                "gpu_e2e_ms": gpu_s * 1e3, "gpu_pairs_per_s": len(pairs) / gpu_s, "gpu_tops_e2e": ops / gpu_s / 1e12,
+                "cpu_ms": cpu_s * 1e3, "cpu_pairs_per_s": len(pairs) / cpu_s, "speedup_e2e": cpu_s / gpu_s,
+                "match_lists_equal_cv2": bool(same), "match_lists_equal_golden": golden_ok,
+                "h2d_bytes": int(sum(h.nbytes for h in host)), "d2h_bytes": int(ctx.last_d2h_bytes)}
+            if sched == "consecutive":
+                tot_pairs += len(pairs); tot_gpu += gpu_s; tot_cpu += cpu_s
+    line = {"metric": "image pairs/s on the reference's bundled datasets (consecutive pairs, SIFT kNN k=2 + ratio), end to end",
+            "value": tot_pairs / tot_gpu, "unit": "pairs/s", "n_gpus": 1, "steps": max(3, args.steps), "warmup": 2,
+            "ms_per_step": tot_gpu * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "bundled datasets (fixtures: SIFT descriptors of dataset/desktop, crazyhorse, dog)",
+            "config": {"workload": "BASELINE.json configs[0-1]: matching of dataset/desktop (5 images), crazyhorse (7), dog (16) "
+                                   "as the reference schedules it, host CV_32F descriptors in, host DMatch lists out"},
+            "e2e": {"value": tot_pairs / tot_gpu, "unit": "pairs/s", "ms_per_step": tot_gpu * 1e3,
+                    "api": "sfm_upload_descriptors_async(pinned CV_32F) + sfm_match_pairs + sfm_fetch_matches"},
+            "cpu_baseline": {"value": tot_pairs / tot_cpu, "unit": "pairs/s", "cores": cv2.getNumThreads(), "kind": "reference",
+                             "sample": f"all {tot_pairs} consecutive pairs, cv2 {cv2.__version__} batchDistance(K=2,NORM_L2) + restated filter"},
+            "datasets": out}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -862,7 +940,7 @@ def main():
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-self-check", action="store_true")
-    ap.add_argument("--workload", default="allpairs", choices=["allpairs", "pair65536", "geometry"])
+    ap.add_argument("--workload", default="allpairs", choices=["allpairs", "pair65536", "geometry", "datasets"])
     ap.add_argument("--points", type=int, default=4_000_000)
     ap.add_argument("--views", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -889,6 +967,8 @@ def main():
         run_pair65536(args, rank, local_rank, world)
     elif args.workload == "geometry":
         run_geometry(args, rank, local_rank, world)
+    elif args.workload == "datasets":
+        run_datasets(args, rank, local_rank, world)
     else:
         run_b200(args, rank, local_rank, world)
 

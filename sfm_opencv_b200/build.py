@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsfm_b200.so")
-SOURCES = ["match_knn.cu", "match_hamming.cu", "match_finalize.cu", "geometry.cu", "host_io.cu", "capi.cu"]
+SOURCES = ["match_knn.cu", "match_hamming.cu", "match_hamming_tc.cu", "match_finalize.cu", "geometry.cu", "host_io.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "shared",

@@ -42,6 +42,11 @@ cudaError_t launch_build_items(const int2* ordoff, int n_pairs, const PairDesc* 
 // match_hamming.cu
 cudaError_t launch_bin_pack(const uint8_t* src, int n, int bytes, int row0, uint8_t* bank,
                             cudaStream_t s);
+cudaError_t launch_bin_expand_tc(const uint8_t* src, int n, int bytes, int row0, uint8_t* bank,
+                                 int32_t* ckey, cudaStream_t s);
+cudaError_t launch_hamming2_tc(const CUtensorMap& tmap, const int32_t* ckey, const PairDesc* pairs,
+                               const int2* items, int n_items, int dot_equal, Knn2* knn_out, int n_sms,
+                               cudaStream_t stream);
 cudaError_t launch_hamming2_knn(const uint8_t* bank, const PairDesc* pairs, const int2* items,
                                 int n_items, int n_splits, int2* partial, int64_t n_rows,
                                 Knn2* knn, cudaStream_t s);
@@ -160,6 +165,12 @@ struct sfm_ctx {
   bool bank_ready = false;
   bool bank_binary = false;   // false: u8 x 128 (NORM_L2); true: 128-byte expanded rows (NORM_HAMMING2)
   DevBuf partial;             // NORM_HAMMING2: per-split top-2 of every query row
+  // NORM_HAMMING2 on the tensor cores (match_hamming_tc.cu; SFM_HAMMING_MODE=0 selects the
+  // CUDA-core kernel): a second bank of 768-byte tetrahedron rows + its tensor map
+  int hamming_mode = 1;
+  DevBuf desc_tc;
+  CUtensorMap tmap_tc;
+  int bin_bytes = 0;          // descriptor length of the binary bank
   CUtensorMap tmap;   // u8 bank, box = 128 rows x 128 bytes, 128-byte swizzle
 
   // matching scratch
@@ -289,6 +300,15 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     }
     ctx->knn_mode = static_cast<int>(v);
   }
+  if (const char* m = getenv("SFM_HAMMING_MODE")) {
+    // A/B switch of the two exact NORM_HAMMING2 kernels: 0 = CUDA cores (XOR / POPC) always,
+    // 1 = tensor cores when the call has enough work items to fill the SMs (default), 2 = always
+    if (strcmp(m, "0") != 0 && strcmp(m, "1") != 0 && strcmp(m, "2") != 0) {
+      sfm_destroy(ctx);
+      return bail(SFM_E_INVALID, "SFM_HAMMING_MODE must be 0, 1 or 2");
+    }
+    ctx->hamming_mode = m[0] - '0';
+  }
   if (err) *err = SFM_OK;
   return ctx;
 }
@@ -306,7 +326,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_tab, &ctx->pairs,
-                    &ctx->partial, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->desc_tc, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -354,9 +374,12 @@ int sfm_timer_stop(sfm_ctx* ctx, float* ms) {
 }
 
 // ----------------------------------------------------------------------------- upload
-static int make_tmap(sfm_ctx* ctx, CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows) {
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kDim), rows};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kDim)};
+// row_bytes: 128 (SIFT bank) or 768 (tetrahedron rows of the tensor-core HAMMING2 bank: the box is
+// one 128-byte K-chunk of 128 rows)
+static int make_tmap(sfm_ctx* ctx, CUtensorMap* tm, void* base, uint64_t rows, uint32_t box_rows,
+                     uint32_t row_bytes = kDim) {
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_bytes), rows};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_bytes)};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kDim), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = ctx->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
@@ -976,6 +999,15 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
   const size_t img_bytes = (static_cast<size_t>(max_n) * bytes + 255) / 256 * 256;
   CK(ctx->stage.ensure(2 * img_bytes + 512));
   CK(cudaMemsetAsync(ctx->desc.p, 0, static_cast<size_t>(rows) * kBinRowBytes, ctx->stream));
+  constexpr size_t kTcRowBytes = 768;                        // 6 K-chunks of 128 s8 (match_hamming_tc.cu)
+  if (ctx->hamming_mode >= 1) {
+    CK(ctx->desc_tc.ensure(static_cast<size_t>(rows) * kTcRowBytes));
+    CK(ctx->ckey.ensure(static_cast<size_t>(rows) * 4));
+    CK(cudaMemsetAsync(ctx->desc_tc.p, 0, static_cast<size_t>(rows) * kTcRowBytes, ctx->stream));
+    int rc = make_tmap(ctx, &ctx->tmap_tc, ctx->desc_tc.p, static_cast<uint64_t>(rows), kTileN, kTcRowBytes);
+    if (rc) return rc;
+  }
+  ctx->bin_bytes = bytes;
   for (int i = 0; i < n_img; ++i) {
     uint8_t* st = ctx->stage.as<uint8_t>() + (i & 1) * img_bytes;
     const size_t nb = static_cast<size_t>(n_desc[i]) * bytes;
@@ -983,6 +1015,11 @@ int sfm_upload_descriptors_bin(sfm_ctx* ctx, int n_img, const uint8_t* const* de
     CK(cudaMemcpyAsync(st, desc_u8[i], nb, cudaMemcpyHostToDevice, ctx->stream));
     CK(launch_bin_pack(st, n_desc[i], bytes, ctx->img_row0[i], ctx->desc.as<uint8_t>(), ctx->stream));
     ctx->launches += 1;
+    if (ctx->hamming_mode >= 1) {
+      CK(launch_bin_expand_tc(st, n_desc[i], bytes, ctx->img_row0[i], ctx->desc_tc.as<uint8_t>(),
+                              ctx->ckey.as<int32_t>(), ctx->stream));
+      ctx->launches += 2;
+    }
   }
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->bank_binary = true;
@@ -1124,7 +1161,16 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
     ctx->launches += 1;
   }
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  if (ctx->bank_binary) {
+  if (ctx->bank_binary && ctx->hamming_mode >= 1 &&
+      (ctx->hamming_mode == 2 || n_items >= ctx->n_sms / 2)) {
+    // NORM_HAMMING2 on the tensor cores: one persistent CTA per SM over (pair, 128-row query block)
+    // items; small calls that cannot fill the SMs that way take the CUDA-core kernel below, which
+    // splits the train images
+    CK(launch_hamming2_tc(ctx->tmap_tc, ctx->ckey.as<int32_t>(), ctx->pairs.as<PairDesc>(),
+                          ctx->items.as<int2>(), static_cast<int>(n_items), 12 * ctx->bin_bytes,
+                          ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+    if (n_items > 0) ctx->launches += 1;
+  } else if (ctx->bank_binary) {
     // NORM_HAMMING2: split every train image over enough blocks to fill the device
     int n_splits = 1;
     if (n_items > 0) {

@@ -772,10 +772,16 @@ cudaError_t launch_triangulate(const float* P, const float* P_host, const float*
   ProjParam pp;
   if (P_host != nullptr && n_views <= kMaxViewsParam) {
     for (int i = 0; i < n_views * 12; ++i) pp.p[i] = static_cast<double>(P_host[i]);
-    if (n_views == 2)
-      triangulate_kernel<true, 2><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
-    else
-      triangulate_kernel<true, 0><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
+    // view count as a template argument: the loop over the views unrolls and every projection
+    // entry becomes a constant-bank operand of its DFMA (the generic loop fetches them with LDC)
+    const int grid = geometry_grid(n_pts, n_sms);
+    switch (n_views) {
+#define SFM_TRI_CASE(V) \
+      case V: triangulate_kernel<true, V><<<grid, 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz); break;
+      SFM_TRI_CASE(2) SFM_TRI_CASE(3) SFM_TRI_CASE(4) SFM_TRI_CASE(5) SFM_TRI_CASE(6) SFM_TRI_CASE(7) SFM_TRI_CASE(8)
+#undef SFM_TRI_CASE
+      default: triangulate_kernel<true, 0><<<grid, 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
+    }
   } else {
     triangulate_kernel<false, 0><<<geometry_grid(n_pts, n_sms), 256, 0, s>>>(pp, P, xy, n_views, n_pts, X4, xyz);
   }

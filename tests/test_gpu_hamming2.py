@@ -1,12 +1,33 @@
 """GPU parity (through the C ABI) of the NORM_HAMMING2 path -- the configuration the live
 reference runs (AKAZE + BFMatcher(NORM_HAMMING2), NViewReconstuct.cpp:797,876) -- against
-the CPU oracle and the AKAZE fixture of the bundled desktop dataset.  Bit-exact."""
+the CPU oracle and the AKAZE fixture of the bundled desktop dataset.  Bit-exact.
+Every test runs on both exact kernels: the CUDA-core XOR / POPC kernel (SFM_HAMMING_MODE=0) and
+the tensor-core kernel over tetrahedron-coded s8 rows (SFM_HAMMING_MODE=2: also for calls too
+small for the default rule to pick it)."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import matching as M
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["cuda_cores", "tensor_cores"])
+def ctx(request):
+    import sfm_opencv_b200 as sfm
+    old = os.environ.get("SFM_HAMMING_MODE")
+    os.environ["SFM_HAMMING_MODE"] = "0" if request.param == "cuda_cores" else "2"
+    try:
+        c = sfm.Context(0)
+    finally:
+        if old is None:
+            del os.environ["SFM_HAMMING_MODE"]
+        else:
+            os.environ["SFM_HAMMING_MODE"] = old
+    yield c
+    c.close()
 
 
 def _rand_bin(n, width, seed):
