@@ -357,18 +357,36 @@ def extras(ctx, hbm_gbs, peak_src, cpu=True):
     except Exception as e:                                   # pragma: no cover
         out["geometry"] = {"error": repr(e)}
     try:
-        # the live reference configuration: binary descriptors, NORM_HAMMING2 (AKAZE-sized: 61 B)
+        # the live reference configuration: binary descriptors, NORM_HAMMING2 (AKAZE-sized: 61 B),
+        # on both exact kernels (same context class, SFM_HAMMING_MODE picks the kernel)
+        import sfm_opencv_b200 as sfm
         rng = np.random.default_rng(0)
         nb, nd = 16, 8192
         bank = [rng.integers(0, 256, (nd, 61), dtype=np.uint8) for _ in range(nb)]
-        ctx.upload_descriptors(bank, norm="hamming2")
-        pairs = all_pairs(nb)
-        ctx.match_pairs_resident(pairs)
-        best = min(ctx.match_pairs_resident(pairs)[1:] for _ in range(3))
-        out["hamming2_16x8192_allpairs"] = {
-            "knn_ms": best[0], "total_ms": best[1], "image_pairs_per_s": len(pairs) / (best[1] * 1e-3),
-            "descriptor_pairs_per_s": len(pairs) * nd * nd / (best[0] * 1e-3),
-            "note": "CUDA-core XOR/POPC kernel, 16 words per descriptor pair"}
+        pairs = np.asarray(all_pairs(nb), np.int32)
+        ham = {}
+        for name, mode in (("tensor_cores", "1"), ("cuda_cores", "0")):
+            os.environ["SFM_HAMMING_MODE"] = mode
+            try:
+                hc = sfm.Context(ctx.device)
+            finally:
+                del os.environ["SFM_HAMMING_MODE"]
+            hc.upload_descriptors(bank, norm="hamming2")
+            hc.match_pairs_resident(pairs)
+            best = min(hc.match_pairs_resident(pairs)[1:] for _ in range(3))
+            tot, _, _ = hc.match_pairs_resident(pairs)
+            ham[name] = {"knn_ms": best[0], "total_ms": best[1], "image_pairs_per_s": len(pairs) / (best[1] * 1e-3),
+                         "descriptor_pairs_per_s": len(pairs) * nd * nd / (best[0] * 1e-3), "matches": int(tot)}
+            hc.close()
+        # tensor pipe: 732 useful (768 stored) s8 dimensions per descriptor pair
+        dp = ham["tensor_cores"]["descriptor_pairs_per_s"]
+        ham["tensor_cores"]["roofline"] = {"bound": "tensor", "achieved": 2.0 * 732 * dp / 1e12, "peak": INT8_DENSE_TOPS,
+                                           "unit": "TOP/s", "frac": 2.0 * 732 * dp / 1e12 / INT8_DENSE_TOPS,
+                                           "frac_with_padding_dims": 2.0 * 768 * dp / 1e12 / INT8_DENSE_TOPS}
+        ham["same_match_count"] = bool(ham["tensor_cores"]["matches"] == ham["cuda_cores"]["matches"])
+        ham["note"] = ("tensor_cores: tetrahedron-coded s8 rows, tcgen05 kind::i8 (match_hamming_tc.cu); "
+                       "cuda_cores: XOR / POPC kernel, 16 words per descriptor pair (match_hamming.cu)")
+        out["hamming2_16x8192_allpairs"] = ham
     except Exception as e:                                   # pragma: no cover
         out["hamming2"] = {"error": repr(e)}
     return out
