@@ -92,11 +92,28 @@ __device__ __forceinline__ int group_max(const uint32_t* r) {
 }
 
 // Close a packed-key window that started at train column `base`: merge its top-2 into the
-// (value, index) pairs and restart the window.
+// (value, index) pairs and restart the window.  Windows are closed in ascending column order, so
+// every index of the window is larger than every index already in (g1, g2): on equal values the
+// older entry wins and the lexicographic order reduces to a strict compare of the values.  Merge
+// of two sorted pairs: 3 compares + 6 selects instead of two general insertions.
 __device__ __forceinline__ void close_window(RowTop2& s, int base) {
   constexpr int kMask = (1 << kColBits) - 1;
+#ifdef SFM_GENERAL_WINDOW_CLOSE
   insert_vi(s, s.m1 >> kColBits, base + (s.m1 & kMask));
   insert_vi(s, s.m2 >> kColBits, base + (s.m2 & kMask));
+#else
+  const int v1 = s.m1 >> kColBits, i1 = base + (s.m1 & kMask);
+  const int v2 = s.m2 >> kColBits, i2 = base + (s.m2 & kMask);   // (v1, i1) <= (v2, i2)
+  const bool c1 = v1 < s.g1v, c2 = v2 < s.g1v, c3 = v1 < s.g2v;
+  // second of the merge: new best took the lead -> old best against the window's second;
+  // otherwise the window's best against the old second
+  const int sv = c1 ? (c2 ? v2 : s.g1v) : (c3 ? v1 : s.g2v);
+  const int si = c1 ? (c2 ? i2 : s.g1i) : (c3 ? i1 : s.g2i);
+  s.g1v = c1 ? v1 : s.g1v;
+  s.g1i = c1 ? i1 : s.g1i;
+  s.g2v = sv;
+  s.g2i = si;
+#endif
   s.m1 = INT32_MAX;
   s.m2 = INT32_MAX;
 }
