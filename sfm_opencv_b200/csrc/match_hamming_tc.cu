@@ -171,21 +171,32 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
           tma_load_2d(sA + kc * kHtChunkBytes, &tmap, bar_a_full, kc * kDim, q_row);
       }
       __syncwarp();
-      for (int t = 0; t < ntiles; ++t, ++tile_seq) {
-        const int row = pd.t_row0 + t * kTileN;
-        for (int kc = 0; kc < kHtChunks; ++kc) {
-          // ring of the tile's parity; cr = chunks that ring has seen so far
-          const uint32_t cr = (tile_seq >> 1) * kHtChunks + kc;
-          const uint32_t stage = (tile_seq & 1) * kHtRing + cr % kHtRing;
-          mbar_wait(bar_empty(stage), ((cr / kHtRing) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_full(stage), kHtChunkBytes + (kc == 0 ? kTileN * 4 : 0));
-            tma_load_2d(sB + stage * kHtChunkBytes, &tmap, bar_full(stage), kc * kDim, row);
-            if (kc == 0)
-              bulk_load_1d(sCk + (tile_seq % kHtCkSlots) * (kTileN * 4), ckey + row, kTileN * 4, bar_full(stage));
+      // Two tiles in flight, one per MMA issuer: the chunks of tiles t and t + 1 are requested in
+      // the order t[0..2], t+1[0..2], t[3..5], t+1[3..5] so that both issuers have operands at the
+      // same time (tile after tile, the second issuer would only start when the first is done, and
+      // a single issuing thread leaves the tensor pipe idle during its commit / wait bubbles).
+      // Inside a ring the order stays (tile, chunk), which is what the issuers expect.
+      for (int t = 0; t < ntiles; t += 2) {
+        const int pair_tiles = ntiles - t < 2 ? 1 : 2;
+        for (int h = 0; h < 2; ++h) {
+          for (int u = 0; u < pair_tiles; ++u) {
+            const uint32_t ts = tile_seq + u;
+            const int row = pd.t_row0 + (t + u) * kTileN;
+            for (int kc = h * kHtRing; kc < (h + 1) * kHtRing; ++kc) {
+              const uint32_t cr = (ts >> 1) * kHtChunks + kc;       // chunks this tile's ring has seen
+              const uint32_t stage = (ts & 1) * kHtRing + cr % kHtRing;
+              mbar_wait(bar_empty(stage), ((cr / kHtRing) & 1) ^ 1);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full(stage), kHtChunkBytes + (kc == 0 ? kTileN * 4 : 0));
+                tma_load_2d(sB + stage * kHtChunkBytes, &tmap, bar_full(stage), kc * kDim, row);
+                if (kc == 0)
+                  bulk_load_1d(sCk + (ts % kHtCkSlots) * (kTileN * 4), ckey + row, kTileN * 4, bar_full(stage));
+              }
+              __syncwarp();
+            }
           }
-          __syncwarp();
         }
+        tile_seq += pair_tiles;
       }
     }
   } else if (warp == kHtMmaWarp0 || warp == kHtMmaWarp0 + 1) {
