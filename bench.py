@@ -623,7 +623,10 @@ def run_b200(args, rank, local_rank, world):
                     ctx.bank_push_range(first, count, k, tag)
                     for d in range(1, world):
                         r = (rank - d) % world               # the peer that pushes to this rank first
-                        ctx.bank_pull_commit(r, row[r][0], row[r][1], k, tag)
+                        ctx.bank_pull_commit(r, row[r][0], 0, k, tag)      # wait for r's flag only ...
+                    r_first, r_end = row[0][0], row[-1][0] + row[-1][1]
+                    ctx.bank_commit(r_first, first - r_first, overlap=True)         # ... then commit the region's
+                    ctx.bank_commit(first + count, r_end - first - count, overlap=True)   # two peer ranges at once
                 return ctx.match_pairs(my_pairs, copy=False)
             bt = ctx.bank_as_torch()
             for k, row in enumerate(regions):

@@ -219,7 +219,10 @@ SFM_API int sfm_peer_connect(sfm_ctx* ctx, int my_rank, int n_ranks,
                              const void* handles /* n_ranks x SFM_PEER_HANDLE_BYTES, rank order */);
 SFM_API int sfm_peer_disconnect(sfm_ctx* ctx);
 SFM_API int sfm_bank_ready_async(sfm_ctx* ctx, uint32_t tag);
-/* slot: 0..14, the region's index -- one flag per (slot, source rank) in every mailbox. */
+/* slot: 0..14, the region's index -- one flag per (slot, source rank) in every mailbox.
+ * sfm_bank_pull_commit_async with n_img = 0 only waits for src_rank's flag: the parts of several
+ * peers that are contiguous in the bank can then be committed by ONE sfm_bank_commit_async (a
+ * region needs two: the peers in front of and behind this rank's own part). */
 SFM_API int sfm_bank_push_range_async(sfm_ctx* ctx, int first_img, int n_img, int slot, uint32_t tag);
 SFM_API int sfm_bank_pull_commit_async(sfm_ctx* ctx, int src_rank, int first_img, int n_img, int slot,
                                        uint32_t tag);
