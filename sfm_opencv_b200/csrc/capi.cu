@@ -504,7 +504,7 @@ static int pack_images(sfm_ctx* ctx, int first, int n, const void* const* desc, 
     CK(launch_pack_rows(f32, src, ctx->img_n[i], ctx->img_row0[i], ctx->desc.as<uint8_t>(),
                         ctx->norm.as<int32_t>(), ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                         ctx->flags.as<uint32_t>(), up));
-    ctx->launches += 3;
+    ctx->launches += 1;
     if (record_events) {
       CK(cudaEventRecord(ctx->img_ev[i], up));                        // image i is resident after this
       ctx->img_evid[i] = i;

@@ -20,67 +20,66 @@ constexpr uint32_t kFlagNorm = 4u;
 // float sqrt is injective on integers below 2^22: require |q|^2 + |t|^2 < 2^22
 constexpr int kMaxNorm = (1 << 21) - 1;
 
-// One warp per descriptor row. src = float rows (is_f32) or u8 rows of ONE image;
-// dst rows are in padded bank coordinates starting at row0.
-// kStore = false: the u8 rows are already in the bank (written by a peer copy / collective,
-// sfm_bank_commit); only their norms and keys are derived.
+// One launch per image: a block of 4 warps owns 8 consecutive rows of the image's PADDED range
+// (two rows per warp), i.e. exactly one 8-row group of the kNN filter.  src = float rows (kF32)
+// or u8 rows of ONE image; dst rows are in padded bank coordinates starting at row0 (a multiple
+// of 256).  Rows [n, n_pad) are padding: zero descriptor (the bank is memset), sentinel norm.
+// The block also writes the group's minimum norm (gmin8), so an upload costs one kernel per image
+// (it was three: pack, pad, group minima -- 600 launches in front of a 200-image step).
+// kStore = false: the u8 rows are already in the bank (sfm_bank_commit's single-image form).
 template <bool kF32, bool kStore>
-__global__ void pack_rows_kernel(const void* __restrict__ src, int n, int row0,
-                                 uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
-                                 int32_t* __restrict__ ckey, uint32_t* __restrict__ flags) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= n) return;
-  uint32_t packed;
+__global__ void __launch_bounds__(128)
+pack_rows_kernel(const void* __restrict__ src, int n, int n_pad, int row0,
+                 uint8_t* __restrict__ desc, int32_t* __restrict__ norm,
+                 int32_t* __restrict__ ckey, int32_t* __restrict__ gmin8,
+                 uint32_t* __restrict__ flags) {
+  __shared__ int32_t s_norm[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t bad = 0;
-  if constexpr (kF32) {
-    const float4 v = reinterpret_cast<const float4*>(src)[static_cast<size_t>(r) * 32 + lane];
-    const float f[4] = {v.x, v.y, v.z, v.w};
-    packed = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float x = f[k];
-      if (!(x >= 0.0f && x <= 255.0f)) bad |= kFlagRange;        // also catches NaN
-      else if (x != rintf(x)) bad |= kFlagNotIntegral;
-      const uint32_t b = static_cast<uint32_t>(fminf(fmaxf(x, 0.0f), 255.0f));
-      packed |= b << (8 * k);
+  for (int k2 = 0; k2 < 2; ++k2) {
+    const int r = blockIdx.x * 8 + warp * 2 + k2;
+    if (r >= n_pad) continue;                      // n_pad is a multiple of 8: whole blocks only
+    int s = kNormPad;
+    if (r < n) {
+      uint32_t packed;
+      if constexpr (kF32) {
+        const float4 v = reinterpret_cast<const float4*>(src)[static_cast<size_t>(r) * 32 + lane];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x = f[k];
+          if (!(x >= 0.0f && x <= 255.0f)) bad |= kFlagRange;        // also catches NaN
+          else if (x != rintf(x)) bad |= kFlagNotIntegral;
+          const uint32_t b = static_cast<uint32_t>(fminf(fmaxf(x, 0.0f), 255.0f));
+          packed |= b << (8 * k);
+        }
+      } else {
+        packed = reinterpret_cast<const uint32_t*>(src)[static_cast<size_t>(r) * 32 + lane];
+      }
+      if constexpr (kStore)
+        reinterpret_cast<uint32_t*>(desc)[static_cast<size_t>(row0 + r) * 32 + lane] = packed;
+      s = __dp4a(packed, packed, 0u);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (s > kMaxNorm) bad |= kFlagNorm;
     }
-  } else {
-    packed = reinterpret_cast<const uint32_t*>(src)[static_cast<size_t>(r) * 32 + lane];
-  }
-  if constexpr (kStore)
-    reinterpret_cast<uint32_t*>(desc)[static_cast<size_t>(row0 + r) * 32 + lane] = packed;
-  int s = __dp4a(packed, packed, 0u);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (s > kMaxNorm) bad |= kFlagNorm;
-  if (lane == 0) {
-    norm[row0 + r] = s;
-    ckey[row0 + r] = (s << kColBits) | (r & ((1 << kColBits) - 1));
+    if (lane == 0) {
+      norm[row0 + r] = s;
+      ckey[row0 + r] = (s << kColBits) | (r & ((1 << kColBits) - 1));
+      s_norm[warp * 2 + k2] = s;
+    }
   }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if (bad && lane == 0) atomicOr(flags, bad);
-}
-
-// Padding rows [n, n_pad) of an image: zero descriptor (bank is memset), sentinel norm.
-__global__ void pad_rows_kernel(int n, int n_pad, int row0, int32_t* __restrict__ norm,
-                                int32_t* __restrict__ ckey) {
-  const int r = n + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_pad) {
-    norm[row0 + r] = kNormPad;
-    ckey[row0 + r] = (kNormPad << kColBits) | (r & ((1 << kColBits) - 1));
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x * 8 < n_pad) {
+    int m = s_norm[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = min(m, s_norm[k]);
+    gmin8[row0 / 8 + blockIdx.x] = m;
   }
-}
-
-// min |row|^2 of every group of 8 bank rows (padding rows carry the sentinel): the bound the
-// kNN epilogue compares raw dot products against
-__global__ void group_min_kernel(const int32_t* __restrict__ norm, int row0, int n_pad,
-                                 int32_t* __restrict__ gmin8) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g * 8 >= n_pad) return;
-  const int4 a = *reinterpret_cast<const int4*>(norm + row0 + g * 8);
-  const int4 b = *reinterpret_cast<const int4*>(norm + row0 + g * 8 + 4);
-  gmin8[row0 / 8 + g] = min(min(min(a.x, a.y), min(a.z, a.w)), min(min(b.x, b.y), min(b.z, b.w)));
 }
 
 // Rows that arrived from another GPU (sfm_bank_commit): norms, keys and sentinels of a whole range
@@ -313,21 +312,18 @@ cudaError_t launch_pack_rows(bool f32, const void* src, int n, int row0, uint8_t
                              cudaStream_t s) {
   // 128-thread CTAs (<= 24 registers per thread): they fit next to a resident kNN CTA (768 threads,
   // 61440 of the SM's 65536 registers), so an asynchronous upload keeps packing while the
-  // matching kernel owns every SM
-  if (n > 0) {
-    const int warps = 4;
-    const int grid = (n + warps - 1) / warps;
-    if (src == nullptr)
-      pack_rows_kernel<false, false><<<grid, warps * 32, 0, s>>>(
-          desc + static_cast<size_t>(row0) * kDim, n, row0, nullptr, norm, ckey, flags);
-    else if (f32)
-      pack_rows_kernel<true, true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
-    else
-      pack_rows_kernel<false, true><<<grid, warps * 32, 0, s>>>(src, n, row0, desc, norm, ckey, flags);
-  }
+  // matching kernel owns every SM.  One launch per image: rows, padding rows and group minima.
   const int n_pad = (n + kRowPad - 1) / kRowPad * kRowPad;
-  if (n_pad > n) pad_rows_kernel<<<(n_pad - n + 127) / 128, 128, 0, s>>>(n, n_pad, row0, norm, ckey);
-  if (n_pad > 0) group_min_kernel<<<(n_pad / 8 + 127) / 128, 128, 0, s>>>(norm, row0, n_pad, gmin8);
+  if (n_pad > 0) {
+    const int grid = n_pad / 8;
+    if (src == nullptr)
+      pack_rows_kernel<false, false><<<grid, 128, 0, s>>>(
+          desc + static_cast<size_t>(row0) * kDim, n, n_pad, row0, nullptr, norm, ckey, gmin8, flags);
+    else if (f32)
+      pack_rows_kernel<true, true><<<grid, 128, 0, s>>>(src, n, n_pad, row0, desc, norm, ckey, gmin8, flags);
+    else
+      pack_rows_kernel<false, true><<<grid, 128, 0, s>>>(src, n, n_pad, row0, desc, norm, ckey, gmin8, flags);
+  }
   return cudaGetLastError();
 }
 
