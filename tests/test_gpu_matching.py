@@ -361,6 +361,28 @@ def test_async_upload_overlapped_with_matching(ctx):
     assert tot == sum(len(x) for x in want)
 
 
+def test_async_upload_many_images_visited_in_arrival_steps(ctx):
+    """30 images: the asynchronous upload is consumed in steps of 8 images (pairs ordered by the
+    arrival of their later image, several launches); results and their caller order are unchanged."""
+    sizes = [300 + 37 * (i % 7) for i in range(30)]
+    bank = [synth.sift_like(n, 400 + i) for i, n in enumerate(sizes)]
+    for j in range(1, len(bank)):
+        bank[j][:60] = bank[j - 1][60:120]
+    rng = np.random.default_rng(5)
+    pairs = M.all_pairs(len(bank))
+    pairs = [pairs[i] for i in rng.permutation(len(pairs))]             # caller order is arbitrary
+    ctx.upload_descriptors(bank)
+    want, wmd, wknn = ctx.match_pairs(pairs, want_knn=True)
+    host = [b.astype(np.float32) for b in bank]
+    ctx.upload_descriptors(host, overlap=True)
+    got, gmd, gknn = ctx.match_pairs(pairs, want_knn=True)
+    assert np.array_equal(gmd.view(np.uint32), wmd.view(np.uint32))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    for a, b in zip(gknn, wknn):
+        assert np.array_equal(a, b)
+
+
 def test_async_upload_reports_validation_errors_at_match(ctx):
     import sfm_opencv_b200 as sfm
     from sfm_opencv_b200 import _capi
