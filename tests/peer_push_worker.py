@@ -66,3 +66,63 @@ def run(rank, inbox, outbox, result):
     except BaseException as e:                    # noqa: BLE001 -- reported to the parent
         result.put((rank, repr(e)))
         raise
+
+
+def run_two_devices(result):
+    """One process, one host thread, contexts on cuda:0 and cuda:1 (the reference is a single
+    process): peer memory is a plain device pointer with peer access enabled; every enqueue is
+    non-blocking (pinned sources), so one thread can drive both ranks of the protocol."""
+    import sfm_opencv_b200 as sfm
+    from oracle import matching as M
+    from oracle import synth
+    from sfm_opencv_b200.sharding import image_regions, shard_pairs_staged, staged_image_ranges
+    try:
+        try:
+            c1 = sfm.Context(1)
+        except sfm.SfmError:
+            result.put("skip")
+            return
+        sizes = [700, 300, 513, 256, 300, 1100, 2, 900, 650, 1500]
+        bank = [synth.sift_like(n, 340 + k) for k, n in enumerate(sizes)]
+        bank[3][:100] = bank[0][:100]
+        pairs = M.all_pairs(len(bank))
+        regions = staged_image_ranges(len(bank), 2, 2)
+        shards = shard_pairs_staged(pairs, sizes, 2, image_regions(len(bank), regions))
+        mine = [[pairs[i] for i in shards[r]] for r in range(2)]
+        with sfm.Context(0) as c0, c1:
+            ranks = (c0, c1)
+            c0.upload_descriptors(bank)
+            want = [match_bytes(c0, mine[r]) for r in range(2)]
+            host = []
+            for r, c in enumerate(ranks):
+                c.bank_layout(sizes)
+                parts = []
+                for row in regions:
+                    first, count = row[r]
+                    part = []
+                    for i in range(first, first + count):
+                        h = c.pinned_empty(bank[i].shape, np.float32, f"img{i}")
+                        h[...] = bank[i]
+                        part.append(h)
+                    parts.append(part)
+                host.append(parts)
+            handles = [c.peer_export() for c in ranks]
+            for r, c in enumerate(ranks):
+                c.peer_connect(r, handles)
+            for tag in (1, 2):
+                for r, c in enumerate(ranks):
+                    c.bank_layout(sizes, overlap=True)
+                    c.bank_ready(tag)
+                    for k, row in enumerate(regions):
+                        first, count = row[r]
+                        c.bank_upload_range(first, host[r][k], overlap=True)
+                        c.bank_push_range(first, count, k, tag)
+                        c.bank_pull_commit(1 - r, row[1 - r][0], row[1 - r][1], k, tag)
+                for r, c in enumerate(ranks):
+                    assert match_bytes(c, mine[r]) == want[r], f"rank {r} step {tag}: results differ"
+            for c in ranks:
+                c.peer_disconnect()
+        result.put("ok")
+    except BaseException as e:                    # noqa: BLE001 -- reported to the parent
+        result.put(repr(e))
+        raise

@@ -623,6 +623,35 @@ def test_peer_push_exchange_two_processes(flags, monkeypatch):
     assert got == {0: "ok", 1: "ok"}, got
 
 
+def test_peer_push_exchange_two_devices_one_process():
+    """The same protocol between two contexts of ONE process on cuda:0 and cuda:1 (needs two GPUs):
+    peer memory is a plain device pointer, one host thread drives both ranks.  In a child process
+    under a timeout, like the two-process test."""
+    import multiprocessing as mp
+    import os
+    import queue
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import peer_push_worker as W
+    mpc = mp.get_context("spawn")
+    result = mpc.Queue()
+    p = mpc.Process(target=W.run_two_devices, args=(result,))
+    p.start()
+    try:
+        msg = result.get(timeout=150)
+    except queue.Empty:
+        msg = "timeout"
+    finally:
+        p.join(timeout=10)
+        if p.is_alive():
+            p.kill()
+    if msg == "skip":
+        pytest.skip("needs two GPUs")
+    assert msg == "ok", msg
+
+
 def test_peer_connect_refuses_two_contexts_on_one_device(ctx):
     """One process, one device: a stream waiting for a flag may sit in front of the stream that has
     to raise it (shared hardware queues), so the library refuses the connection."""
