@@ -698,8 +698,24 @@ __global__ void flag_write_kernel(volatile uint32_t* p, uint32_t v) {
   __threadfence_system();
   *p = v;
 }
+// Bounded like the kernels' mbarrier waits: a peer that never raises its flag (crashed rank, protocol
+// bug) ends in a trap after 30 s instead of a kernel that spins for ever.  (The stream-memory-operation
+// form of the wait has no such bound: it ends with the process.)
 __global__ void flag_wait_kernel(const volatile uint32_t* p, uint32_t v) {
-  while (static_cast<int32_t>(*p - v) < 0) __nanosleep(200);
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (static_cast<int32_t>(*p - v) < 0) {
+    __nanosleep(200);
+    if ((++spins & 0xffffu) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 30ull * 1000 * 1000 * 1000) {
+        printf("sfm_b200: peer flag %p never reached %u\n", (const void*)p, v);
+        __trap();
+      }
+    }
+  }
   __threadfence_system();
 }
 

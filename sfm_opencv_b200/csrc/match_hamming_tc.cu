@@ -15,11 +15,11 @@
 //   warp 0        TMA producer: the block's 6 A chunks once per item (96 KB, resident), then the
 //                 train image as 128-row x 128-byte B chunks (16 KB) through an mbarrier ring,
 //                 plus 512 B of column keys per tile
-//   warps 4, 5    MMA issuers by tile parity: 6 chunks x 4 MMAs (128x128x32) per tile into one of
-//                 4 TMEM accumulators (4 x 128 columns); two issuers hide each other's
-//                 commit / wait bubbles (tools/exp_probe.py).  Each issuer has its own ring of
-//                 3 B stages: with one shared ring the even-tile warp would wait for a stage's
-//                 phase two rounds ahead, and a parity wait cannot tell round r from round r + 2
+//   warps 4..6    MMA issuers, tile ts belongs to issuer ts % 3: 6 chunks x 4 MMAs (128x128x32) per
+//                 tile into one of 4 TMEM accumulators (4 x 128 columns); the issuers hide each
+//                 other's commit / wait bubbles (tools/exp_probe.py).  Each issuer has its own ring
+//                 of 2 B stages: with one shared ring an issuer would wait for a stage's phase two
+//                 rounds ahead, and a parity wait cannot tell round r from round r + 2
 //   warps 8..15   epilogue: 2 column halves x 4 TMEM lane quarters; a thread owns one query row
 //                 and 64 columns of every tile and keeps the exact top-2 as packed keys
 //                 ((-2 dot) << 10 | column: an integer min is OpenCV's (distance, lower index)
@@ -43,8 +43,14 @@ namespace sfm {
 constexpr int kHtChunks = 6;                     // K-chunks of 128 bytes per descriptor (768 dims)
 constexpr int kHtRowBytes = kHtChunks * kDim;    // 768
 constexpr int kHtM = 128;                        // query rows per work item
-constexpr int kHtStages = 6;                     // B chunk stages (16 KB each): one ring of 3 per tile parity
-constexpr int kHtRing = kHtStages / 2;
+#ifndef SFM_HT_ISSUERS
+#define SFM_HT_ISSUERS 3
+#endif
+constexpr int kHtIssuers = SFM_HT_ISSUERS;       // MMA issuing warps: tile ts belongs to issuer ts % kHtIssuers
+constexpr int kHtStages = 6;                     // B chunk stages (16 KB each): one ring per issuer
+constexpr int kHtRing = kHtStages / kHtIssuers;  // stages per ring
+static_assert(kHtIssuers == 2 || kHtIssuers == 3, "issuers");
+static_assert(kHtChunks % kHtRing == 0, "a tile's chunks are requested in groups of one ring");
 constexpr int kHtAccBufs = 4;                    // TMEM accumulators (128 columns each)
 constexpr int kHtCkSlots = 16;                   // ring of per-tile column keys (512 B each)
 constexpr int kHtMmaWarp0 = 4, kHtEpiWarp0 = 8, kHtEpiWarps = 8;
@@ -137,7 +143,7 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 2 + kHtEpiWarps);        // both MMA warps + every epilogue warp
+    mbar_init(bar_a_empty, kHtIssuers + kHtEpiWarps);   // every MMA warp + every epilogue warp
     for (uint32_t b = 0; b < kHtAccBufs; ++b) {
       mbar_init(bar_t_full(b), 1);
       mbar_init(bar_t_empty(b), kHtEpiWarps);
@@ -171,20 +177,20 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
           tma_load_2d(sA + kc * kHtChunkBytes, &tmap, bar_a_full, kc * kDim, q_row);
       }
       __syncwarp();
-      // Two tiles in flight, one per MMA issuer: the chunks of tiles t and t + 1 are requested in
-      // the order t[0..2], t+1[0..2], t[3..5], t+1[3..5] so that both issuers have operands at the
-      // same time (tile after tile, the second issuer would only start when the first is done, and
-      // a single issuing thread leaves the tensor pipe idle during its commit / wait bubbles).
-      // Inside a ring the order stays (tile, chunk), which is what the issuers expect.
-      for (int t = 0; t < ntiles; t += 2) {
-        const int pair_tiles = ntiles - t < 2 ? 1 : 2;
-        for (int h = 0; h < 2; ++h) {
-          for (int u = 0; u < pair_tiles; ++u) {
+      // kHtIssuers tiles in flight, one per MMA issuer: the chunks of tiles t .. t + kHtIssuers - 1 are
+      // requested interleaved, kHtRing chunks of each tile in turn, so that every issuer has operands
+      // at the same time (tile after tile, the next issuer would only start when the previous one is
+      // done, and a single issuing thread leaves the tensor pipe idle during its commit / wait
+      // bubbles).  Inside a ring the order stays (tile, chunk), which is what the issuers expect.
+      for (int t = 0; t < ntiles; t += kHtIssuers) {
+        const int group = ntiles - t < kHtIssuers ? ntiles - t : kHtIssuers;
+        for (int h = 0; h < kHtChunks / kHtRing; ++h) {
+          for (int u = 0; u < group; ++u) {
             const uint32_t ts = tile_seq + u;
             const int row = pd.t_row0 + (t + u) * kTileN;
             for (int kc = h * kHtRing; kc < (h + 1) * kHtRing; ++kc) {
-              const uint32_t cr = (ts >> 1) * kHtChunks + kc;       // chunks this tile's ring has seen
-              const uint32_t stage = (ts & 1) * kHtRing + cr % kHtRing;
+              const uint32_t cr = (ts / kHtIssuers) * kHtChunks + kc;   // chunks this tile's ring has seen
+              const uint32_t stage = (ts % kHtIssuers) * kHtRing + cr % kHtRing;
               mbar_wait(bar_empty(stage), ((cr / kHtRing) & 1) ^ 1);
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full(stage), kHtChunkBytes + (kc == 0 ? kTileN * 4 : 0));
@@ -196,11 +202,11 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
             }
           }
         }
-        tile_seq += pair_tiles;
+        tile_seq += group;
       }
     }
-  } else if (warp == kHtMmaWarp0 || warp == kHtMmaWarp0 + 1) {
-    // ===================================================== MMA issuers by tile parity
+  } else if (warp >= kHtMmaWarp0 && warp < kHtMmaWarp0 + kHtIssuers) {
+    // ===================================================== MMA issuers: tile ts belongs to issuer ts % kHtIssuers
     const uint32_t mp = warp - kHtMmaWarp0;
     constexpr uint32_t idesc = make_idesc_s8(kHtM, kTileN);
     uint32_t seq = 0, item_seq = 0;                              // tiles / items of this CTA so far
@@ -208,17 +214,17 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
       mbar_wait(bar_a_full, item_seq & 1);
       const uint32_t ntiles = info[item_seq & 1].ntiles;
       const uint32_t end = seq + ntiles;
-      uint32_t ts = seq + ((seq & 1) != mp);                     // first tile of this warp's parity
-      if (ts >= end) {                                           // single-tile item of the other parity
+      uint32_t ts = seq + (mp + kHtIssuers - seq % kHtIssuers) % kHtIssuers;   // this warp's first tile
+      if (ts >= end) {                                           // short item: no tile for this warp
         if (elect_one()) mbar_arrive(bar_a_empty);
         __syncwarp();
       }
-      for (; ts < end; ts += 2) {
+      for (; ts < end; ts += kHtIssuers) {
         const uint32_t buf = ts % kHtAccBufs;
         mbar_wait(bar_t_empty(buf), ((ts / kHtAccBufs) & 1) ^ 1);
         const uint32_t d_tmem = tmem_base + buf * kTileN;
         for (uint32_t kc = 0; kc < kHtChunks; ++kc) {
-          const uint32_t cr = (ts >> 1) * kHtChunks + kc;           // this warp's ring, in order
+          const uint32_t cr = (ts / kHtIssuers) * kHtChunks + kc;   // this warp's ring, in order
           const uint32_t stage = mp * kHtRing + cr % kHtRing;
           mbar_wait(bar_full(stage), (cr / kHtRing) & 1);
           tc_fence_after();
@@ -231,7 +237,7 @@ hamming2_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
             umma_commit(bar_empty(stage));
             if (kc == kHtChunks - 1) {
               umma_commit(bar_t_full(buf));
-              if (ts + 2 >= end) umma_commit(bar_a_empty);       // this warp's last tile of the item
+              if (ts + kHtIssuers >= end) umma_commit(bar_a_empty);   // this warp's last tile of the item
             }
           }
           __syncwarp();
