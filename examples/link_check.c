@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
                        (const void*)sfm_estimate_normals, (const void*)sfm_save_structure,
                        (const void*)sfm_write_ply_binary, (const void*)sfm_triangulate_batch_timed,
                        (const void*)sfm_reproject_residuals_timed, (const void*)sfm_probe_i8_peak,
-                       (const void*)sfm_probe_fp64_peak, (const void*)sfm_launch_count,
+                       (const void*)sfm_probe_fp64_peak, (const void*)sfm_launch_count, (const void*)sfm_last_rechecked_rows,
                        (const void*)sfm_timer_start, (const void*)sfm_timer_stop, (const void*)sfm_sync,
                        (const void*)sfm_bank_layout, (const void*)sfm_bank_upload_range,
                        (const void*)sfm_bank_commit, (const void*)sfm_bank_image_rows,

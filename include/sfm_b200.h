@@ -409,6 +409,10 @@ SFM_API int sfm_probe_fp64_peak(sfm_ctx* ctx, int iters, double* tflops);
 
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 SFM_API int64_t sfm_launch_count(const sfm_ctx* ctx);
+/* Rows of the last match-only call (knn_raw == NULL) that the ratio-driven sweep could not decide and
+ * that were recomputed exactly on the CUDA cores before the filter passes (diagnostics; 0 when the
+ * sweep was not used: knn_raw requested, SFM_PRUNE_MODE=0, binary descriptors). */
+SFM_API int64_t sfm_last_rechecked_rows(const sfm_ctx* ctx);
 
 /* CUDA-event stopwatch on the context's own stream (torch.cuda.Event only sees torch's
  * stream): sfm_timer_start records, sfm_timer_stop records + synchronises and returns the

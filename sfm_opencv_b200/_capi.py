@@ -53,6 +53,7 @@ SYMBOLS = {
     "sfm_reproject_residuals_timed": (_i, [_vp, _pd, _pd, _i, _pd, _i64, _pi, _pi, _pf, _i64, _d, _pd, _pd, _i, _pf]),
     "sfm_probe_i8_peak": (_i, [_vp, _i, _pd]),
     "sfm_launch_count": (_i64, [_vp]),
+    "sfm_last_rechecked_rows": (_i64, [_vp]),
     "sfm_timer_start": (_i, [_vp]),
     "sfm_timer_stop": (_i, [_vp, _pf]),
     "sfm_sync": (_i, [_vp]),

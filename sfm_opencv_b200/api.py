@@ -111,6 +111,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.sfm_launch_count(self._h))
 
+    @property
+    def last_rechecked_rows(self) -> int:
+        """Rows of the last match-only call that were recomputed exactly (sfm_last_rechecked_rows)."""
+        return int(self._lib.sfm_last_rechecked_rows(self._h))
+
     # ------------------------------------------------------------------ matching
     def upload_descriptors(self, descriptor_for_all, norm: str = "l2", overlap: bool = False):
         """descriptor_for_all: list of [n_i,128] arrays, float32 (as cv::SIFT gives) or uint8.

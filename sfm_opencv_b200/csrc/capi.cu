@@ -19,7 +19,11 @@ namespace sfm {
 // match_knn.cu
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
-                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, cudaStream_t stream);
+                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, int32_t* flag_count,
+                        int2* flag_rows, int flag_cap, cudaStream_t stream);
+cudaError_t launch_recheck_rows(const uint8_t* desc, const int32_t* norm, const PairDesc* pairs,
+                                const int2* rows, const int32_t* count, int cap, Knn2* knn, int n_sms,
+                                cudaStream_t s);
 cudaError_t launch_i8_peak(int iters, int n_sms, cudaStream_t stream);
 bool knn2_mode_valid(int mode);
 // match_finalize.cu
@@ -160,6 +164,13 @@ struct sfm_ctx {
   DevBuf ordoff;
   std::vector<int32_t> h_order;                // processing order of the pairs (L2 blocking)
   std::vector<int32_t> h_bucket, h_key;        // counting sort of the pairs by block key
+  // ratio-driven match-only sweep (match_knn.cu kPrune): rows it could not decide -- [0]: count,
+  // entries from byte 16 -- are recomputed by recheck_rows_kernel; SFM_PRUNE_MODE=0 switches it off
+  DevBuf flagged;
+  int flag_cap = 0;
+  int prune_mode = 1;
+  bool pruned_last = false;                    // the last match_device call used the list
+  int32_t last_flagged = 0;                    // ... and flagged this many rows
   std::vector<std::pair<int64_t, int>> h_groups;   // per L2 block: first work item, last image read
   int64_t bank_rows = 0;
   bool bank_ready = false;
@@ -300,6 +311,14 @@ sfm_ctx* sfm_create(int device_id, int* err) {
     }
     ctx->knn_mode = static_cast<int>(v);
   }
+  if (const char* m = getenv("SFM_PRUNE_MODE")) {
+    // A/B switch of the ratio-driven match-only sweep (identical match lists either way)
+    if (strcmp(m, "0") != 0 && strcmp(m, "1") != 0) {
+      sfm_destroy(ctx);
+      return bail(SFM_E_INVALID, "SFM_PRUNE_MODE must be 0 or 1");
+    }
+    ctx->prune_mode = m[0] - '0';
+  }
   if (const char* m = getenv("SFM_HAMMING_MODE")) {
     // A/B switch of the two exact NORM_HAMMING2 kernels: 0 = CUDA cores (XOR / POPC) always,
     // 1 = tensor cores when the call has enough work items to fill the SMs (default), 2 = always
@@ -326,7 +345,7 @@ void sfm_destroy(sfm_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->desc, &ctx->norm, &ctx->ckey, &ctx->gmin8, &ctx->flags, &ctx->stage, &ctx->img_tab, &ctx->pairs,
-                    &ctx->partial, &ctx->desc_tc, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
+                    &ctx->partial, &ctx->desc_tc, &ctx->flagged, &ctx->ordoff, &ctx->kp, &ctx->gsel, &ctx->gjtab, &ctx->gjac, &ctx->gflag, &ctx->gseg, &ctx->items, &ctx->knn, &ctx->counts, &ctx->offsets, &ctx->min_dist,
                     &ctx->out, &ctx->knn_f, &ctx->gP, &ctx->gxy, &ctx->gX4, &ctx->gxyz,
                     &ctx->gext, &ctx->gcam, &ctx->gpts, &ctx->gci, &ctx->gpi, &ctx->gobs,
                     &ctx->gres, &ctx->gbc, &ctx->gcost};
@@ -349,6 +368,7 @@ void sfm_host_free(void* p) {
 }
 
 int64_t sfm_launch_count(const sfm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t sfm_last_rechecked_rows(const sfm_ctx* ctx) { return ctx && ctx->pruned_last ? ctx->last_flagged : 0; }
 
 int sfm_sync(sfm_ctx* ctx) {
   if (!ctx) return SFM_E_INVALID;
@@ -1186,6 +1206,18 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
                           ctx->bank_binary ? 128 : kTileM, ctx->items.as<int2>(), ctx->stream));
     ctx->launches += 1;
   }
+  // ratio-driven match-only sweep: list of the rows it cannot decide (recomputed below)
+  const bool prune = !ctx->bank_binary && !need_knn && ctx->prune_mode != 0 && ctx->knn_mode == 1 &&
+                     ratio > 0.0 && ratio <= 1.0 && n_items > 0;
+  ctx->pruned_last = prune;
+  if (prune) {
+    ctx->flag_cap = static_cast<int>(std::min<int64_t>(std::max<int64_t>(65536, rows / 8), 1 << 26));
+    CK(ctx->flagged.ensure(16 + sizeof(int2) * static_cast<size_t>(ctx->flag_cap)));
+    CK(cudaMemsetAsync(ctx->flagged.p, 0, 16, ctx->stream));
+  }
+  int32_t* const flag_count = prune ? ctx->flagged.as<int32_t>() : nullptr;
+  int2* const flag_rows = prune ? reinterpret_cast<int2*>(ctx->flagged.as<uint8_t>() + 16) : nullptr;
+  const int flag_cap = prune ? ctx->flag_cap : 0;
   if (time_it) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (ctx->bank_binary && ctx->hamming_mode >= 1 &&
       (ctx->hamming_mode == 2 || n_items >= ctx->n_sms / 2)) {
@@ -1231,23 +1263,42 @@ static int match_device(sfm_ctx* ctx, const int32_t* pair_q, const int32_t* pair
         CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                        ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>() + first,
                        static_cast<int>(last - first), ctx->knn.as<Knn2>(), ctx->n_sms,
-                       need_knn ? 0.0 : ratio, ctx->stream));
+                       need_knn ? 0.0 : ratio, flag_count, flag_rows, flag_cap, ctx->stream));
         ctx->launches += 1;
       }
     } else {
       CK(launch_knn2(ctx->knn_mode, ctx->tmap, ctx->ckey.as<int32_t>(), ctx->gmin8.as<int32_t>(),
                      ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), ctx->items.as<int2>(),
                      static_cast<int>(n_items), ctx->knn.as<Knn2>(), ctx->n_sms,
-                     need_knn ? 0.0 : ratio, ctx->stream));
+                     need_knn ? 0.0 : ratio, flag_count, flag_rows, flag_cap, ctx->stream));
       if (n_items > 0) ctx->launches += 1;
     }
+  }
+  if (prune) {
+    CK(launch_recheck_rows(ctx->desc.as<uint8_t>(), ctx->norm.as<int32_t>(), ctx->pairs.as<PairDesc>(), flag_rows,
+                           flag_count, flag_cap, ctx->knn.as<Knn2>(), ctx->n_sms, ctx->stream));
+    ctx->launches += 1;
   }
   if (time_it) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
   CK(launch_filter(ctx->knn.as<Knn2>(), ctx->pairs.as<PairDesc>(), n_pairs, ratio, dist_floor,
                    gate_mult, nullptr, ctx->min_dist.as<float>(), ctx->counts.as<int32_t>(),
                    ctx->offsets.as<int64_t>(), ctx->stream));
   ctx->launches += (n_pairs > 0 ? 2 : 1);
-  return finish_upload(ctx);     // no-op unless an asynchronous upload is pending: its verdict
+  int rc = finish_upload(ctx);   // no-op unless an asynchronous upload is pending: its verdict
+  if (rc || !prune) return rc;
+  // more undecided rows than the list holds (adversarial input: it holds an eighth of all rows): the
+  // surplus was not recomputed, so the whole call is repeated with the plain match-only sweep
+  int32_t n_flagged = 0;
+  CK(cudaMemcpyAsync(&n_flagged, flag_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->last_flagged = n_flagged;
+  if (n_flagged <= flag_cap) return SFM_OK;
+  const int saved = ctx->prune_mode;
+  ctx->prune_mode = 0;
+  rc = match_device(ctx, pair_q, pair_t, q_first, q_count, n_pairs, ratio, dist_floor, gate_mult, total_rows,
+                    time_it, need_knn);
+  ctx->prune_mode = saved;
+  return rc;
 }
 
 // Writes the kept matches of the last sfm_match_pairs* call (still resident) to the host.

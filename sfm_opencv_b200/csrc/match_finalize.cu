@@ -132,6 +132,79 @@ cudaError_t launch_commit_rows(const uint8_t* desc, const int32_t* img_row0, con
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------- recheck
+// Rows the ratio-driven sweep of match_knn.cu (kPrune) could not decide: exact k = 2 search of ONE
+// query row against its whole train image on the CUDA cores (a few rows in 10^4: a candidate nearest
+// neighbour whose fail range reaches into columns that were skipped).  One warp per row: every lane
+// holds the query descriptor in 32 registers and walks every 32nd train row (16-byte loads; the 32
+// rows of a step are 4 KB of consecutive bank memory), u8 dot products by dp4a, per-lane exact top-2
+// in (value, index) order, shuffle merge, and the row of the kNN table is overwritten.
+__device__ __forceinline__ void top2_push(int v, int i, int& v1, int& i1, int& v2, int& i2) {
+  const bool b1 = (v < v1) | ((v == v1) & (i < i1));
+  const bool b2 = (v < v2) | ((v == v2) & (i < i2));
+  v2 = b1 ? v1 : (b2 ? v : v2);
+  i2 = b1 ? i1 : (b2 ? i : i2);
+  v1 = b1 ? v : v1;
+  i1 = b1 ? i : i1;
+}
+
+__global__ void __launch_bounds__(128)
+recheck_rows_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ norm,
+                    const PairDesc* __restrict__ pairs, const int2* __restrict__ rows,
+                    const int32_t* __restrict__ count, int cap, Knn2* __restrict__ knn) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n = min(*count, cap);
+  for (int e = warp; e < n; e += n_warps) {
+    const int2 pr = rows[e];
+    const PairDesc pd = pairs[pr.x];
+    const uint4* q4 = reinterpret_cast<const uint4*>(desc + static_cast<size_t>(pd.q_row0 + pr.y) * kDim);
+    uint32_t q[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint4 v = __ldg(q4 + k);
+      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+    }
+    int v1 = INT32_MAX, i1 = INT32_MAX, v2 = INT32_MAX, i2 = INT32_MAX;
+    for (int j = lane; j < pd.nt; j += 32) {
+      const uint4* t4 = reinterpret_cast<const uint4*>(desc + static_cast<size_t>(pd.t_row0 + j) * kDim);
+      uint32_t dot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 t = __ldg(t4 + k);
+        dot = __dp4a(q[4 * k], t.x, dot);
+        dot = __dp4a(q[4 * k + 1], t.y, dot);
+        dot = __dp4a(q[4 * k + 2], t.z, dot);
+        dot = __dp4a(q[4 * k + 3], t.w, dot);
+      }
+      top2_push(__ldg(norm + pd.t_row0 + j) - 2 * static_cast<int>(dot), j, v1, i1, v2, i2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int a = __shfl_xor_sync(0xffffffffu, v1, o), ai = __shfl_xor_sync(0xffffffffu, i1, o);
+      const int b = __shfl_xor_sync(0xffffffffu, v2, o), bi = __shfl_xor_sync(0xffffffffu, i2, o);
+      top2_push(a, ai, v1, i1, v2, i2);
+      top2_push(b, bi, v1, i1, v2, i2);
+    }
+    if (lane == 0) {
+      const int nq2 = norm[pd.q_row0 + pr.y];
+      Knn2 out;
+      out.j0 = i1;
+      out.j1 = i2;
+      out.d0 = v1 + nq2;
+      out.d1 = v2 + nq2;
+      *reinterpret_cast<int4*>(&knn[pd.knn_off + pr.y]) = *reinterpret_cast<int4*>(&out);
+    }
+  }
+}
+
+cudaError_t launch_recheck_rows(const uint8_t* desc, const int32_t* norm, const PairDesc* pairs,
+                                const int2* rows, const int32_t* count, int cap, Knn2* knn, int n_sms,
+                                cudaStream_t s) {
+  recheck_rows_kernel<<<n_sms * 4, 128, 0, s>>>(desc, norm, pairs, rows, count, cap, knn);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------- filter
 __device__ __forceinline__ bool ratio_fails(float d0, float d1, double ratio) {
   // `knn[i][0].distance > 0.6 * knn[i][1].distance`: float promoted to double (:884, :900)

@@ -130,7 +130,8 @@ struct ItemInfo {
   int32_t rows_valid;   // query rows of this block that exist (<= 256)
   int32_t norm_row;     // bank row of the block's first query row
   int32_t t_row0;       // bank row of the train image's first row
-  int32_t pad[2];
+  int32_t pair;         // pair index and first row of the block within the pair (flagged rows, kPrune)
+  int32_t row0;
   int64_t knn_row;      // first output row of the block
 };
 
@@ -228,11 +229,35 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[8 * kG], uint32
 // rows that pass, their distances and min_dist are exactly those of the full search; for rows
 // that fail, Knn2::j1 / d1 may name a column that is not the true second neighbour (it is never
 // better than the true one, so the row fails the real test too).
-template <int kMode, bool kMatchOnly = false>
+//
+// kPrune (match-only): the bound follows the RATIO TEST itself.  With (D0, D1) the squared distances of
+// the two nearest columns known for the row (its own and its row partner's, exact columns):
+//   F, D0 > ratio^2 D1 (fails with what is known): a column can only matter as a new nearest neighbour
+//      that PASSES, i.e. below ratio^2 * D0 -- whatever lies in [ratio^2 D0, D0) would become the
+//      nearest neighbour of a row that still fails (its second is at most D0).  Bound: ratio^2 D0.
+//   P, D0 <= ratio^2 D1 (passes with what is known): what matters is a better nearest neighbour or a
+//      column that makes the test fail, both below D0 / ratio^2.  Bound: D0 / ratio^2.
+// (always together with the exact rule "nothing at or above the known second".)  For random
+// descriptors the F bound is far below every distance, so a row hits only on a real candidate.
+// One case is undecidable inside the sweep: a row that ends in state P with a nearest neighbour D0
+// whose "fail range" [D0, D0 / ratio^2) reaches into what was skipped earlier under an F bound
+// (D0 / ratio^2 > the smallest F bound the row ever used).  Such rows are appended to a list and
+// recomputed exactly by recheck_rows_kernel before the filter passes read them; everything else is
+// exact: a row whose true nearest neighbour was skipped fails the real test (it is >= ratio^2 times a
+// known column), and a row stored as failing fails (its stored columns are real).
+struct PruneParams {
+  int32_t* count;       // number of flagged rows (may exceed cap: the host then repeats the call unpruned)
+  int2* rows;           // (pair, row within the pair)
+  int32_t cap;
+  float inv_ratio2;     // (1 + margin) / ratio^2
+};
+template <int kMode, bool kMatchOnly = false, bool kPrune = false>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict__ ckey,
             const int32_t* __restrict__ gmin8, const int32_t* __restrict__ norm, const PairDesc* __restrict__ pairs,
-            const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg, float ratio2) {
+            const int2* __restrict__ items, int n_items, Knn2* __restrict__ knn_out, int dbg, float ratio2,
+            const PruneParams prune) {
+  static_assert(!kPrune || (kMatchOnly && kMode == 1), "the ratio-driven bound belongs to the match-only sweep");
   extern __shared__ uint8_t smem_raw[];
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -315,6 +340,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           info[abuf].rows_valid = pd.nq - mblk * kTileM;
           info[abuf].norm_row = pd.q_row0 + mblk * kTileM;
           info[abuf].t_row0 = pd.t_row0;
+          info[abuf].pair = it.x;
+          info[abuf].row0 = mblk * kTileM;
           info[abuf].knn_row = pd.knn_off + static_cast<int64_t>(mblk) * kTileM;
           mbar_arrive_expect_tx(bar_a_full(abuf), kABytes);
           tma_load_2d(sA + abuf * kABytes, &tmap, bar_a_full(abuf), 0, pd.q_row0 + mblk * kTileM);
@@ -427,6 +454,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
     for (int item = blockIdx.x; item < n_items && !SFM_DBG(2); item += gridDim.x) {
       RowTop2 st = {INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MAX};
       int ntiles = 1, rows_valid = 0, norm_row = 0;
+      [[maybe_unused]] int pair_id = 0, row0 = 0;
+      [[maybe_unused]] int smin = INT32_MAX;       // kPrune: smallest F bound this thread skipped under
       int64_t knn_row = 0;
       if constexpr (kMode <= 1) {
         // ---- sweep: a thread's share of a tile is a 32-column piece A and (except for the last
@@ -439,6 +468,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         rows_valid = info[abuf].rows_valid;
         norm_row = info[abuf].norm_row;
         knn_row = info[abuf].knn_row;
+        if constexpr (kPrune) {
+          pair_id = info[abuf].pair;
+          row0 = info[abuf].row0;
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_empty(abuf));
         abuf ^= 1;
@@ -531,7 +564,17 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
                 if constexpr (kMatchOnly) {
                   // squared distances are exact integers < 2^22: exact in float
                   const float d0 = static_cast<float>(j1 + nq2), d1 = static_cast<float>(j2 + nq2);
-                  if (d0 > ratio2 * d1) bound = min(bound, j1);
+                  if constexpr (kPrune) {
+                    if (d0 > ratio2 * d1) {                  // F: only a passing new nearest neighbour matters
+                      const int tf = static_cast<int>(ratio2 * d0) + 1 - nq2;
+                      bound = min(bound, tf);
+                      smin = min(smin, tf);
+                    } else {                                 // P: better neighbours and whatever makes the test fail
+                      bound = min(bound, static_cast<int>(d0 * prune.inv_ratio2) + 2 - nq2);
+                    }
+                  } else {
+                    if (d0 > ratio2 * d1) bound = min(bound, j1);
+                  }
                 }
               }
             }
@@ -603,6 +646,9 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
       const uint32_t slot = merge_row + mslot * ((kParts - 1) * kTileM * 16);
       mslot ^= 1;
       if (part > 0) sts_v4(slot + (part - 1) * (kTileM * 16), st.g1v, st.g1i, st.g2v, st.g2i);
+      if constexpr (kPrune) {
+        if (part > 0) sts_v2(share_row + 16, static_cast<uint32_t>(smin), 0u);   // bytes 16.. of the row's slot are free
+      }
       asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * kParts) : "memory");
       if (part == 0) {
 #pragma unroll
@@ -613,6 +659,16 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         }
         if (row_in_blk < rows_valid) {
           const int nq2 = __ldg(norm + norm_row + row_in_blk);
+          if constexpr (kPrune) {
+            // the row ends in state P with a fail range that reaches into what an F bound skipped:
+            // not decidable from what was kept -- recheck_rows_kernel recomputes the row
+            smin = min(smin, lds_v2(share_row + 16).x);
+            const float d0 = static_cast<float>(st.g1v + nq2), d1 = static_cast<float>(st.g2v + nq2);
+            if (d0 <= ratio2 * d1 && static_cast<int>(d0 * prune.inv_ratio2) + 2 - nq2 > smin) {
+              const int idx = atomicAdd(prune.count, 1);
+              if (idx < prune.cap) prune.rows[idx] = make_int2(pair_id, row0 + row_in_blk);
+            }
+          }
           SFM_ASSERT(st.g1i >= 0 && st.g2i >= 0 && st.g1i != st.g2i && st.g1v <= st.g2v && st.g1v + nq2 >= 0,
                      "top-2 of a row is not two distinct, ordered train rows");
           Knn2 out;
@@ -721,16 +777,16 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int variant)
 // The shared-memory opt-in is a per-device attribute of the kernel: it is set on every launch
 // (a host-side table lookup), so contexts on several devices -- one per host thread, as
 // INTEGRATION.md recommends -- each get it.
-template <int kMode, bool kMatchOnly>
+template <int kMode, bool kMatchOnly, bool kPrune = false>
 static cudaError_t launch_knn2_mode(const CUtensorMap& tmap, const int32_t* ckey, const int32_t* gmin8,
                                     const int32_t* norm, const PairDesc* pairs, const int2* items,
                                     int n_items, Knn2* knn_out, int grid, int dbg, float ratio2,
-                                    cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(knn2_kernel<kMode, kMatchOnly>,
+                                    cudaStream_t stream, const PruneParams& prune = PruneParams{nullptr, nullptr, 0, 0.f}) {
+  cudaError_t e = cudaFuncSetAttribute(knn2_kernel<kMode, kMatchOnly, kPrune>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes);
   if (e != cudaSuccess) return e;
-  knn2_kernel<kMode, kMatchOnly><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(
-      tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, dbg, ratio2);
+  knn2_kernel<kMode, kMatchOnly, kPrune><<<grid, kKnnThreads, kKnnSmemBytes, stream>>>(
+      tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, dbg, ratio2, prune);
   return cudaGetLastError();
 }
 
@@ -743,9 +799,12 @@ bool knn2_mode_valid(int mode) {
 }
 
 // match_ratio > 0: the caller needs match lists only (see kMatchOnly); 0: exact kNN rows.
+// flag_count / flag_rows / flag_cap (nullable): list of the rows the ratio-driven sweep (kPrune) could not
+// decide; with a list the match-only call prunes, without one it runs the plain match-only sweep.
 cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
                         const int32_t* gmin8, const int32_t* norm, const PairDesc* pairs, const int2* items,
-                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, cudaStream_t stream) {
+                        int n_items, Knn2* knn_out, int n_sms, double match_ratio, int32_t* flag_count,
+                        int2* flag_rows, int flag_cap, cudaStream_t stream) {
   if (!knn2_mode_valid(mode)) return cudaErrorInvalidValue;
   const int grid = n_items < n_sms ? n_items : n_sms;
   if (grid <= 0) return cudaSuccess;
@@ -763,6 +822,12 @@ cudaError_t launch_knn2(int mode, const CUtensorMap& tmap, const int32_t* ckey,
     // the real test is (double)sqrtf(d0) > ratio * (double)sqrtf(d1): two float roundings of
     // 6e-8 each, squared; a relative margin of 1e-5 on ratio^2 keeps "fails for sure" sure
     const float ratio2 = static_cast<float>(match_ratio * match_ratio * (1.0 + 1e-5));
+    if (flag_count != nullptr && flag_rows != nullptr && flag_cap > 0) {
+      const PruneParams prune = {flag_count, flag_rows, flag_cap,
+                                 static_cast<float>((1.0 + 1e-5) / (match_ratio * match_ratio))};
+      return launch_knn2_mode<1, true, true>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, ratio2,
+                                             stream, prune);
+    }
     return launch_knn2_mode<1, true>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, ratio2, stream);
   }
   return launch_knn2_mode<1, false>(tmap, ckey, gmin8, norm, pairs, items, n_items, knn_out, grid, dbg, 0.f, stream);
