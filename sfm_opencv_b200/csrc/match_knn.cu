@@ -108,6 +108,9 @@ static_assert(4 * kRegsProd + 4 * kRegsMma + kEpiWarps * kRegsEpi <= (kFirstEpiW
 __host__ __device__ constexpr int part_col0(int p) { return kParts == 2 ? 64 * p : 48 * p; }
 __host__ __device__ constexpr int part_bgroups(int p) { return kParts == 2 ? 4 : (p < 2 ? 2 : 0); }
 constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-key window (8)
+#ifndef SFM_PRUNE_COLD_TILES
+#define SFM_PRUNE_COLD_TILES 2                  // unfiltered tiles at the start of a ratio-driven (kPrune) sweep
+#endif
 #ifndef SFM_COLD_WINDOWS
 #define SFM_COLD_WINDOWS 1                      // windows at the start of a sweep that skip the filter
 #endif
@@ -492,8 +495,10 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         uint32_t rb[kBG > 0 ? 8 * kBG : 8];
         // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
         // behind the inner loop, not behind a per-tile test
-        for (int w0 = w_first; w0 < w_last; w0 += kWinTiles) {
-        const int wend = min(w0 + kWinTiles, ntiles);
+        // a window ends at the next multiple of kWinTiles (its keys carry the column modulo 1024) or
+        // where the sweep ends -- the cold sweep may stop inside a window
+        for (int w0 = w_first, wend; w0 < w_last; w0 = wend) {
+        wend = min((w0 / kWinTiles + 1) * kWinTiles, w_last);
         for (int t = w0; t < wend; ++t) {
           if constexpr (kBG == 4) tmem_ld_x32(t_addr + buf * (2 * kTileN) + 32, rb);   // piece B in flight
           if constexpr (kBG == 2) tmem_ld_x16(t_addr + buf * (2 * kTileN) + 32, rb);
@@ -536,7 +541,7 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           {
             // close the 1024-column window, then tighten the bound, also with the row
             // partners' top-2 (ties with the partners' columns go by index: + 1)
-            close_window(st, w0 * kTileN);
+            close_window(st, (w0 / kWinTiles * kWinTiles) * kTileN);
             int bound = st.g2v;
             if (kMode == 1) {
               // the row's second best over ALL column parts bounds what can still enter: second
@@ -585,7 +590,8 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         // The first windows of a sweep run unfiltered: while the top-2 of a row is still cold
         // 65-100 % of the groups hit for some row of the warp, and testing them first (max tree,
         // compare, vote, branch) costs more than it saves.
-        constexpr int kCold = kMode == 1 ? SFM_COLD_WINDOWS * kWinTiles : 0;
+        // (the ratio-driven bound needs two known columns, not a warm top-2: a short cold sweep)
+        constexpr int kCold = kMode != 1 ? 0 : (kPrune ? SFM_PRUNE_COLD_TILES : SFM_COLD_WINDOWS * kWinTiles);
         const int cold = min(kCold, ntiles);
         auto sweeps = [&](auto bg_tag) {
           if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, bg_tag, 0, cold);
