@@ -111,6 +111,15 @@ constexpr int kWinTiles = (1 << kColBits) / kTileN;   // train tiles per packed-
 #ifndef SFM_PRUNE_COLD_TILES
 #define SFM_PRUNE_COLD_TILES 2                  // unfiltered tiles at the start of a ratio-driven (kPrune) sweep
 #endif
+#ifndef SFM_SHARE_VOTE
+#define SFM_SHARE_VOTE 1                        // ratio-driven sweep: one vote per 64-column share of a tile
+#endif
+#ifndef SFM_RELEASE_FIRST
+#define SFM_RELEASE_FIRST 1                     // ratio-driven sweep: TMEM buffer handed back in front of piece A
+#endif
+#ifndef SFM_PRUNE_SEED
+#define SFM_PRUNE_SEED 1                        // ratio-driven sweep: 8 seed columns per thread instead of unfiltered tiles
+#endif
 #ifndef SFM_COLD_WINDOWS
 #define SFM_COLD_WINDOWS 1                      // windows at the start of a sweep that skip the filter
 #endif
@@ -220,6 +229,17 @@ __device__ __forceinline__ void chunk_update(const uint32_t (&r)[8 * kG], uint32
       }
     }
   }
+}
+
+// smallest possible value |t|^2 - 2 q.t over a piece of kG groups (group maxima against the groups'
+// minimum norms): the piece holds a candidate for a row iff this is below the row's bound
+template <int kG>
+__device__ __forceinline__ int share_min(const uint32_t (&r)[8 * kG], uint32_t gm_addr, int neg2) {
+  static_assert(kG == 4, "a 32-column piece");
+  const int4 nn = lds_v4(gm_addr);
+  return min(__vimin3_s32(group_max(&r[0]) * neg2 + nn.x, group_max(&r[8]) * neg2 + nn.y,
+                          group_max(&r[16]) * neg2 + nn.z),
+             group_max(&r[24]) * neg2 + nn.w);
 }
 
 // kMatchOnly (mode 1 only): the caller wants match lists, not the raw kNN rows.  A row whose
@@ -493,6 +513,11 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
           constexpr bool kPre = decltype(pre_tag)::value;
           constexpr int kBG = decltype(bg_tag)::value;       // groups of piece B: 4, 2 or 0
         uint32_t rb[kBG > 0 ? 8 * kBG : 8];
+          // ratio-driven sweep: quiet tiles are the rule, so ONE vote covers the thread's whole
+          // 64-column share; a share with a hit falls back to the piece / group tests
+          constexpr bool kQuiet = kPrune && kM == 1 && kPre && kBG == 4;
+          constexpr bool kShareVote = SFM_SHARE_VOTE && kQuiet;
+          constexpr bool kReleaseFirst = SFM_RELEASE_FIRST && kQuiet;
         // tiles in windows of kWinTiles (one packed-key window): the window bookkeeping sits
         // behind the inner loop, not behind a per-tile test
         // a window ends at the next multiple of kWinTiles (its keys carry the column modulo 1024) or
@@ -511,19 +536,28 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
             __syncwarp();
             mbar_arrive_elected(bar_te + 16 * buf);
           };
-          if constexpr (kBG == 0) {
+          if constexpr (kReleaseFirst) release();               // both pieces in registers: two tiles of slack
+          if constexpr (kShareVote) {
+            const int va = share_min<4>(ra, gm_addr, neg2);
+            if constexpr (!kReleaseFirst) release();
+            const int vb = share_min<4>(rb, gm_addr + 16, neg2);
+            if (__any_sync(0xffffffffu, min(va, vb) < st.bv)) {
+              chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st);
+              chunk_update<kM, kPre, 4>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+            }
+          } else if constexpr (kBG == 0) {
             release();                                          // piece A is the whole share
             chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st);
           } else if constexpr (kPre && !SFM_PRE_RELEASE_MID) {
             chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st);
-            release();
+            if constexpr (!kReleaseFirst) release();
           } else {
             // released from inside piece A (after its votes, before its inserts): piece B has
             // landed by then, and the MMA of tile t+2 starts a third of a tile earlier (+0.9 %)
             chunk_update<kM, kPre, 4>(ra, ck_addr, gm_addr, neg2, st, release);
           }
           const uint32_t nbuf = buf ^ 1, nphase = bphase ^ buf; // phase flips when buf wraps to 0
-          if constexpr (kBG > 0) chunk_update<kM, kPre, kBG>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
+          if constexpr (kBG > 0 && !kShareVote) chunk_update<kM, kPre, kBG>(rb, ck_addr + 128, gm_addr + 16, neg2, st);
           // Tile t+1 is asked for only now, not before piece B: the warps that share a TMEM
           // buffer drift apart by their hit counts, and the MMA of tile t+1 starts when the
           // slowest of them released tile t-1 -- waiting half a tile later keeps 44 % of the
@@ -591,10 +625,32 @@ knn2_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __restrict_
         // 65-100 % of the groups hit for some row of the warp, and testing them first (max tree,
         // compare, vote, branch) costs more than it saves.
         // (the ratio-driven bound needs two known columns, not a warm top-2: a short cold sweep)
-        constexpr int kCold = kMode != 1 ? 0 : (kPrune ? SFM_PRUNE_COLD_TILES : SFM_COLD_WINDOWS * kWinTiles);
+        constexpr bool kSeed = kPrune && SFM_PRUNE_SEED != 0;
+        constexpr int kCold = kMode != 1 || kSeed ? 0 : (kPrune ? SFM_PRUNE_COLD_TILES : SFM_COLD_WINDOWS * kWinTiles);
         const int cold = min(kCold, ntiles);
+        if constexpr (kSeed) {
+          // No unfiltered tiles at all: the ratio-driven bound only needs two known columns, whichever.
+          // The first group of the thread's share of tile 0 is inserted unconditionally, the bound
+          // follows from those 8 columns alone, and the filtered sweep starts at tile 0 (looking at a
+          // column twice is harmless: keys are unique and the knock-out insert keeps the top-2 of a SET).
+          group_insert(&ra[0], ck_base + (tile_seq % kCkSlots) * kCkBytes, st);
+          constexpr int kNone = (1 << 21) - 1;               // a padding row's value (kNormPad)
+          const int v1 = st.m1 >> kColBits, v2 = st.m2 >> kColBits;
+          int bound = v2;
+          if (v2 < kNone) {
+            const float d0 = static_cast<float>(v1 + nq2), d1 = static_cast<float>(v2 + nq2);
+            if (d0 > ratio2 * d1) {
+              const int tf = static_cast<int>(ratio2 * d0) + 1 - nq2;
+              bound = min(bound, tf);
+              smin = min(smin, tf);
+            } else {
+              bound = min(bound, static_cast<int>(d0 * prune.inv_ratio2) + 2 - nq2);
+            }
+          }
+          st.bv = bound;
+        }
         auto sweeps = [&](auto bg_tag) {
-          if (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, bg_tag, 0, cold);
+          if constexpr (kCold > 0) sweep(std::integral_constant<int, 0>{}, std::false_type{}, bg_tag, 0, cold);
           if (kMatchOnly || ntiles >= kPreVoteTiles) sweep(std::integral_constant<int, kMode>{}, std::true_type{}, bg_tag, cold, ntiles);
           else sweep(std::integral_constant<int, kMode>{}, std::false_type{}, bg_tag, cold, ntiles);
         };

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import matching as M
+from ratio_sweep_model import undecidable_case
 from test_oracle_matching import descriptor_pair, knn_sha
 
 pytestmark = pytest.mark.gpu
@@ -147,3 +148,38 @@ def test_max_norm_rows_and_rejected_rows(ctx):
     with pytest.raises(sfm.SfmError) as e:
         ctx.upload_descriptors([q, bad])
     assert e.value.code == _capi.SFM_E_RANGE
+
+
+def test_undecidable_rows_are_rechecked(ctx):
+    """Rows the ratio-driven sweep cannot decide (tests/ratio_sweep_model.py: they would PASS with the
+    second neighbour the sweep kept and FAIL with the true one) go through recheck_rows_kernel: the
+    match-only call reports them and returns the exact lists."""
+    q, t = undecidable_case(nq=300, nt=2000)
+    q[7] = t[1500]                                         # one row with a true match
+    ctx.upload_descriptors([q, t])
+    b, bmd, _ = ctx.match_pairs([(0, 1)])
+    # all but the true match, less the warp of the true match (its columns are looked at for all 32 rows)
+    assert 300 - 32 <= ctx.last_rechecked_rows <= 299
+    om, od, omd, _, _ = M.match_features(q, t)
+    assert np.array_equal(b[0]["queryIdx"], om[:, 0]) and np.array_equal(b[0]["trainIdx"], om[:, 1])
+    assert np.array_equal(_bits(b[0]["distance"]), _bits(od)) and _bits(bmd[0]) == _bits(omd)
+    assert len(om) == 1
+    a, amd, _ = ctx.match_pairs([(0, 1)], want_knn=True)   # the exact search never rechecks
+    assert ctx.last_rechecked_rows == 0 and _same_lists(a, b)
+
+
+def test_recheck_list_overflow_repeats_the_call_unpruned(ctx):
+    """More undecidable rows than the recheck list holds (65 536, or an eighth of all query rows): the
+    call is repeated with the plain match-only sweep; lists and min_dist are still exact."""
+    q, t = undecidable_case(nq=17000, nt=1024)
+    good = t.copy()
+    good[300] = q[0]                                       # every query row has an exact copy here
+    ctx.upload_descriptors([q, t, np.roll(t, 1, 0), np.roll(t, 2, 0), np.roll(t, 3, 0), good])
+    pairs = [(0, j) for j in range(1, 6)]
+    b, bmd, _ = ctx.match_pairs(pairs)
+    assert ctx.last_rechecked_rows == 0                    # the sweep's verdicts were thrown away
+    a, amd, _ = ctx.match_pairs(pairs, want_knn=True)
+    assert _same_lists(a, b) and amd.tobytes() == bmd.tobytes()
+    assert [len(m) for m in b] == [0, 0, 0, 0, 17000]
+    om, od, omd, _, _ = M.match_features(q[:512], good)
+    assert np.array_equal(b[4]["trainIdx"][:512], om[:, 1]) and _bits(bmd[4]) == _bits(omd)
