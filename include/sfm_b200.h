@@ -411,7 +411,8 @@ SFM_API int sfm_probe_fp64_peak(sfm_ctx* ctx, int iters, double* tflops);
 SFM_API int64_t sfm_launch_count(const sfm_ctx* ctx);
 /* Rows of the last match-only call (knn_raw == NULL) that the ratio-driven sweep could not decide and
  * that were recomputed exactly on the CUDA cores before the filter passes (diagnostics; 0 when the
- * sweep was not used: knn_raw requested, SFM_PRUNE_MODE=0, binary descriptors). */
+ * sweep was not used: knn_raw requested, binary descriptors, SFM_PRUNE_MODE=0, or a call below the
+ * 2048 work items (256-row query blocks) from which the default SFM_PRUNE_MODE=2 uses it). */
 SFM_API int64_t sfm_last_rechecked_rows(const sfm_ctx* ctx);
 
 /* CUDA-event stopwatch on the context's own stream (torch.cuda.Event only sees torch's

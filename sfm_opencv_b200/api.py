@@ -347,7 +347,7 @@ class Context:
             self._check(rc)
         total = int(offsets[n_pairs])
         raw = self._pinned("matches", max(total, 1) * MATCH_DTYPE.itemsize)
-        out = raw.view(MATCH_DTYPE)[:max(total, 1)]
+        out = raw.view(MATCH_DTYPE)[:total]          # empty when nothing matched (never a stale record)
         if total:
             self._check(self._lib.sfm_fetch_matches(self._h, out.ctypes.data, total))
         if copy:

@@ -133,12 +133,20 @@ cudaError_t launch_commit_rows(const uint8_t* desc, const int32_t* img_row0, con
 }
 
 // ------------------------------------------------------------------------------- recheck
-// Rows the ratio-driven sweep of match_knn.cu (kPrune) could not decide: exact k = 2 search of ONE
-// query row against its whole train image on the CUDA cores (a few rows in 10^4: a candidate nearest
-// neighbour whose fail range reaches into columns that were skipped).  One warp per row: every lane
-// holds the query descriptor in 32 registers and walks every 32nd train row (16-byte loads; the 32
-// rows of a step are 4 KB of consecutive bank memory), u8 dot products by dp4a, per-lane exact top-2
-// in (value, index) order, shuffle merge, and the row of the kNN table is overwritten.
+// Rows the ratio-driven sweep of match_knn.cu (kPrune) could not decide: exact k = 2 search of the
+// query row against its whole train image on the CUDA cores (a few rows in 10^4 on unrelated images,
+// 0.5-2.5 % on the bundled datasets, where about half of the true matches have a fail range that
+// reaches into skipped columns).
+//   1. the list is counting-sorted by pair (recheck_hist / scan_counts / recheck_scatter), so that
+//      rows which read the same train image sit next to each other;
+//   2. recheck_rows_kernel: a block of 8 warps takes 16 consecutive rows; every run of rows of one
+//      pair shares the train image through shared memory: 128-row tiles, loaded once per run with
+//      coalesced 16-byte loads into rows of 144 bytes (conflict-free for the 16-byte reads below).
+//      A warp owns two query rows (2 x 32 registers per lane); a lane takes every 32nd row of the tile,
+//      u8 dot products by dp4a, per-lane exact top-2 in (value, index) order, shuffle merge, and the
+//      row of the kNN table is overwritten.  Per (query, train) pair of rows this reads 64 bytes of
+//      shared memory instead of 8 separate 128-byte lines of L1 (one warp per row on its own, as
+//      first built, cost +4 ms on dataset/dog: 6 200 flagged rows x 18 000 train rows).
 __device__ __forceinline__ void top2_push(int v, int i, int& v1, int& i1, int& v2, int& i2) {
   const bool b1 = (v < v1) | ((v == v1) & (i < i1));
   const bool b2 = (v < v2) | ((v == v2) & (i < i2));
@@ -148,61 +156,140 @@ __device__ __forceinline__ void top2_push(int v, int i, int& v1, int& i1, int& v
   i1 = b1 ? i : i1;
 }
 
-__global__ void __launch_bounds__(128)
-recheck_rows_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ norm,
-                    const PairDesc* __restrict__ pairs, const int2* __restrict__ rows,
-                    const int32_t* __restrict__ count, int cap, Knn2* __restrict__ knn) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(256)
+recheck_hist_kernel(const int2* __restrict__ rows, const int32_t* __restrict__ count, int cap,
+                    int32_t* __restrict__ hist) {
   const int n = min(*count, cap);
-  for (int e = warp; e < n; e += n_warps) {
-    const int2 pr = rows[e];
-    const PairDesc pd = pairs[pr.x];
-    const uint4* q4 = reinterpret_cast<const uint4*>(desc + static_cast<size_t>(pd.q_row0 + pr.y) * kDim);
-    uint32_t q[32];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint4 v = __ldg(q4 + k);
-      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
-    }
-    int v1 = INT32_MAX, i1 = INT32_MAX, v2 = INT32_MAX, i2 = INT32_MAX;
-    for (int j = lane; j < pd.nt; j += 32) {
-      const uint4* t4 = reinterpret_cast<const uint4*>(desc + static_cast<size_t>(pd.t_row0 + j) * kDim);
-      uint32_t dot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint4 t = __ldg(t4 + k);
-        dot = __dp4a(q[4 * k], t.x, dot);
-        dot = __dp4a(q[4 * k + 1], t.y, dot);
-        dot = __dp4a(q[4 * k + 2], t.z, dot);
-        dot = __dp4a(q[4 * k + 3], t.w, dot);
-      }
-      top2_push(__ldg(norm + pd.t_row0 + j) - 2 * static_cast<int>(dot), j, v1, i1, v2, i2);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int a = __shfl_xor_sync(0xffffffffu, v1, o), ai = __shfl_xor_sync(0xffffffffu, i1, o);
-      const int b = __shfl_xor_sync(0xffffffffu, v2, o), bi = __shfl_xor_sync(0xffffffffu, i2, o);
-      top2_push(a, ai, v1, i1, v2, i2);
-      top2_push(b, bi, v1, i1, v2, i2);
-    }
-    if (lane == 0) {
-      const int nq2 = norm[pd.q_row0 + pr.y];
-      Knn2 out;
-      out.j0 = i1;
-      out.j1 = i2;
-      out.d0 = v1 + nq2;
-      out.d1 = v2 + nq2;
-      *reinterpret_cast<int4*>(&knn[pd.knn_off + pr.y]) = *reinterpret_cast<int4*>(&out);
-    }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    atomicAdd(hist + rows[e].x, 1);
+}
+
+__global__ void __launch_bounds__(256)
+recheck_scatter_kernel(const int2* __restrict__ rows, const int32_t* __restrict__ count, int cap,
+                       const int64_t* __restrict__ offs, int32_t* __restrict__ cursor,
+                       int2* __restrict__ sorted) {
+  const int n = min(*count, cap);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int2 r = rows[e];
+    sorted[offs[r.x] + atomicAdd(cursor + r.x, 1)] = r;
   }
 }
 
-cudaError_t launch_recheck_rows(const uint8_t* desc, const int32_t* norm, const PairDesc* pairs,
-                                const int2* rows, const int32_t* count, int cap, Knn2* knn, int n_sms,
-                                cudaStream_t s) {
-  recheck_rows_kernel<<<n_sms * 4, 128, 0, s>>>(desc, norm, pairs, rows, count, cap, knn);
-  return cudaGetLastError();
+// 16- / 4-byte asynchronous copies global -> shared; `ok` false writes zeros without reading
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+               "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+               "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+
+constexpr int kRcWarps = 8;             // warps per block
+constexpr int kRcPerWarp = 2;           // query rows per warp: every 16-byte read of a train row feeds two dot products
+constexpr int kRcRows = kRcWarps * kRcPerWarp;   // rows per block
+constexpr int kRcTile = 128;            // train rows per shared-memory tile
+constexpr int kRcRow16 = kDim / 16 + 1; // 16-byte words per staged row: 128 bytes + 16 of padding
+
+__global__ void __launch_bounds__(kRcWarps * 32)
+recheck_rows_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ norm,
+                    const PairDesc* __restrict__ pairs, const int2* __restrict__ rows,
+                    const int32_t* __restrict__ count, int cap, Knn2* __restrict__ knn) {
+  __shared__ uint4 s_tile[2][kRcTile * kRcRow16];   // double-buffered: tile t+1 lands (cp.async) under tile t
+  __shared__ int32_t s_norm[2][kRcTile];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min(*count, cap);
+  // few rows: one per warp, so that more blocks (and SMs) share them; many: two per warp
+  const int rpb = n <= static_cast<int>(gridDim.x) * kRcWarps ? kRcWarps : kRcRows;
+  for (int chunk = blockIdx.x * rpb; chunk < n; chunk += gridDim.x * rpb) {
+    const int end = min(chunk + rpb, n);
+    for (int start = chunk, run; start < end; start += run) {      // block-uniform
+      const int pair = rows[start].x;
+      run = 1;
+      while (start + run < end && rows[start + run].x == pair) ++run;
+      const PairDesc pd = pairs[pair];
+      // the run's rows go to the warps round-robin: row u of the run belongs to warp u % kRcWarps
+      bool mine[kRcPerWarp];
+      int qrow[kRcPerWarp];
+      uint32_t q[kRcPerWarp][32];
+      int v1[kRcPerWarp], i1[kRcPerWarp], v2[kRcPerWarp], i2[kRcPerWarp];
+#pragma unroll
+      for (int u = 0; u < kRcPerWarp; ++u) {
+        mine[u] = warp + u * kRcWarps < run;
+        qrow[u] = mine[u] ? rows[start + warp + u * kRcWarps].y : 0;
+        const uint4* q4 = reinterpret_cast<const uint4*>(desc + static_cast<size_t>(pd.q_row0 + qrow[u]) * kDim);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint4 v = __ldg(q4 + k);
+          q[u][4 * k] = v.x; q[u][4 * k + 1] = v.y; q[u][4 * k + 2] = v.z; q[u][4 * k + 3] = v.w;
+        }
+        v1[u] = i1[u] = v2[u] = i2[u] = INT32_MAX;
+      }
+      auto stage = [&](int t0, int b) {                              // tile [t0, t0 + 128) -> buffer b, zero-filled past nt
+        for (int i = threadIdx.x; i < kRcTile * 8; i += kRcWarps * 32) {
+          const int r = i >> 3, k = i & 7;
+          const bool ok = t0 + r < pd.nt;
+          cp_async_16(&s_tile[b][r * kRcRow16 + k],
+                      desc + static_cast<size_t>(pd.t_row0 + (ok ? t0 + r : 0)) * kDim + 16 * k, ok);
+        }
+        if (threadIdx.x < kRcTile) {
+          const bool ok = t0 + static_cast<int>(threadIdx.x) < pd.nt;
+          cp_async_4(&s_norm[b][threadIdx.x], norm + pd.t_row0 + (ok ? t0 + threadIdx.x : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      __syncthreads();                                               // the previous run has left both buffers
+      stage(0, 0);
+      for (int t0 = 0, b = 0; t0 < pd.nt; t0 += kRcTile, b ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                             // tile b is visible; buffer b ^ 1 has been read
+        if (t0 + kRcTile < pd.nt) stage(t0 + kRcTile, b ^ 1);
+        if (mine[0]) {                                               // warp-uniform; mine[1] implies mine[0]
+#pragma unroll
+          for (int jj = 0; jj < kRcTile / 32; ++jj) {
+            const int r = lane + 32 * jj, j = t0 + r;
+            uint32_t dot[kRcPerWarp] = {};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint4 t = s_tile[b][r * kRcRow16 + k];
+#pragma unroll
+              for (int u = 0; u < kRcPerWarp; ++u) {
+                dot[u] = __dp4a(q[u][4 * k], t.x, dot[u]);
+                dot[u] = __dp4a(q[u][4 * k + 1], t.y, dot[u]);
+                dot[u] = __dp4a(q[u][4 * k + 2], t.z, dot[u]);
+                dot[u] = __dp4a(q[u][4 * k + 3], t.w, dot[u]);
+              }
+            }
+            if (j < pd.nt) {
+              const int tn = s_norm[b][r];
+#pragma unroll
+              for (int u = 0; u < kRcPerWarp; ++u)
+                top2_push(tn - 2 * static_cast<int>(dot[u]), j, v1[u], i1[u], v2[u], i2[u]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRcPerWarp; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const int a = __shfl_xor_sync(0xffffffffu, v1[u], o), ai = __shfl_xor_sync(0xffffffffu, i1[u], o);
+          const int b = __shfl_xor_sync(0xffffffffu, v2[u], o), bi = __shfl_xor_sync(0xffffffffu, i2[u], o);
+          top2_push(a, ai, v1[u], i1[u], v2[u], i2[u]);
+          top2_push(b, bi, v1[u], i1[u], v2[u], i2[u]);
+        }
+        if (mine[u] && lane == 0) {
+          const int nq2 = norm[pd.q_row0 + qrow[u]];
+          Knn2 out;
+          out.j0 = i1[u];
+          out.j1 = i2[u];
+          out.d0 = v1[u] + nq2;
+          out.d1 = v2[u] + nq2;
+          *reinterpret_cast<int4*>(&knn[pd.knn_off + qrow[u]]) = *reinterpret_cast<int4*>(&out);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------- filter
@@ -418,6 +505,20 @@ cudaError_t launch_filter_write(const Knn2* knn, const PairDesc* pairs, int n_pa
   if (n_pairs > 0)
     filter_write_kernel<<<n_pairs, 256, 0, s>>>(knn, pairs, ratio, dist_floor, gate_mult, min_dist,
                                                 offsets, out, out_cap);
+  return cudaGetLastError();
+}
+
+// work: 2 * n_pairs int32 (histogram, cursors; zeroed here), offs: n_pairs + 1 int64, sorted: cap int2
+cudaError_t launch_recheck_rows(const uint8_t* desc, const int32_t* norm, const PairDesc* pairs, int n_pairs,
+                                const int2* rows, const int32_t* count, int cap, int32_t* work, int64_t* offs,
+                                int2* sorted, Knn2* knn, int n_sms, cudaStream_t s) {
+  if (n_pairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(int32_t) * 2 * static_cast<size_t>(n_pairs), s);
+  if (e != cudaSuccess) return e;
+  recheck_hist_kernel<<<n_sms, 256, 0, s>>>(rows, count, cap, work);
+  scan_counts_kernel<<<1, 1024, 0, s>>>(work, n_pairs, offs);
+  recheck_scatter_kernel<<<n_sms, 256, 0, s>>>(rows, count, cap, offs, work + n_pairs, sorted);
+  recheck_rows_kernel<<<n_sms * 4, kRcWarps * 32, 0, s>>>(desc, norm, pairs, sorted, count, cap, knn);
   return cudaGetLastError();
 }
 

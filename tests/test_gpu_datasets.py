@@ -183,3 +183,34 @@ def test_recheck_list_overflow_repeats_the_call_unpruned(ctx):
     assert [len(m) for m in b] == [0, 0, 0, 0, 17000]
     om, od, omd, _, _ = M.match_features(q[:512], good)
     assert np.array_equal(b[4]["trainIdx"][:512], om[:, 1]) and _bits(bmd[4]) == _bits(omd)
+
+
+def test_prune_mode_auto_small_calls_use_the_plain_sweep(monkeypatch):
+    """Default SFM_PRUNE_MODE=2: a call below 2048 work items (256-row query blocks) runs the plain
+    match-only sweep (nothing is rechecked), a larger one the ratio-driven sweep; the lists are the same
+    as with the sweep forced off."""
+    import sfm_opencv_b200 as sfm
+    from oracle import synth
+    q, t = undecidable_case(nq=300, nt=2000)
+    bank = synth.image_bank(10, 12800, seed0=77)            # 45 pairs x 50 blocks = 2250 work items
+    pairs = M.all_pairs(10)
+    got = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("SFM_PRUNE_MODE", mode)
+        with sfm.Context(0) as c:
+            c.upload_descriptors([q, t])
+            small, smd, _ = c.match_pairs([(0, 1)])
+            assert c.last_rechecked_rows == 0
+            small = (small.flat.tobytes(), smd.tobytes())      # the lists live until the next call
+            c.upload_descriptors(bank)
+            big, bmd, _ = c.match_pairs(pairs)
+            got[mode] = small + (big.flat.tobytes(), big.offsets.tobytes(), bmd.tobytes())
+            assert len(big.flat) > 10000
+    assert got["2"] == got["0"]
+    om, od, omd, _, _ = M.match_features(bank[3], bank[4], knn=M.knn2_cv)
+    monkeypatch.setenv("SFM_PRUNE_MODE", "2")
+    with sfm.Context(0) as c:
+        c.upload_descriptors(bank)
+        b, bmd, _ = c.match_pairs(pairs)
+        p = pairs.index((3, 4))
+        assert np.array_equal(b[p]["trainIdx"], om[:, 1]) and _bits(bmd[p]) == _bits(omd)
