@@ -5,6 +5,7 @@
 //   match_features()            :873-913    match_features_for_all()   :850-871
 //   get_matched_points()        :989-1003   reconstruct()              :1117-1159
 //   ReprojectCost evaluation    :142-184    save_structure()           :186-227
+//   residual-block enumeration  :1187-1211  (enumerate_observations, bundle_adjustment_residuals)
 //
 // No OpenCV types appear here.  The element types are template parameters that only have to be
 // layout-compatible with the OpenCV value types the reference uses (checked with static_assert):
@@ -18,6 +19,7 @@
 #ifndef SFM_B200_HPP
 #define SFM_B200_HPP
 
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -199,6 +201,52 @@ double reproject_residuals(const Context& c, const double intrinsic[4], const st
                                   reinterpret_cast<const double*>(pts3d.data()), static_cast<int64_t>(pts3d.size()),
                                   cam_idx.data(), pt_idx.data(), obs_xy.data(), static_cast<int64_t>(cam_idx.size()),
                                   huber_delta, residuals.data(), &cost));
+  return cost;
+}
+
+// The residual-block order of bundle_adjustment() (:1187-1211): for every image, for every keypoint in
+// order, one observation (camera = image, point = correspond_struct_idx[img][kp], kp.pt) where the
+// index is >= 0.  Host glue, no device work; fills the tables reproject_residuals() takes.
+template <class Point2fT>
+void enumerate_observations(const std::vector<std::vector<int>>& correspond_struct_idx,
+                            const std::vector<std::vector<Point2fT>>& key_points_for_all,
+                            std::vector<int32_t>& cam_idx, std::vector<int32_t>& pt_idx, std::vector<float>& obs_xy) {
+  static_assert(sizeof(Point2fT) == 8, "Point2fT must be layout-compatible with cv::Point2f");
+  if (correspond_struct_idx.size() != key_points_for_all.size())
+    throw Error(SFM_E_INVALID, "enumerate_observations: one index vector per image");
+  cam_idx.clear();
+  pt_idx.clear();
+  obs_xy.clear();
+  for (size_t img = 0; img < correspond_struct_idx.size(); ++img) {
+    const std::vector<int>& ids = correspond_struct_idx[img];
+    if (ids.size() != key_points_for_all[img].size())
+      throw Error(SFM_E_INVALID, "enumerate_observations: one structure index per keypoint");
+    for (size_t kp = 0; kp < ids.size(); ++kp) {
+      if (ids[kp] < 0) continue;
+      const float* xy = reinterpret_cast<const float*>(&key_points_for_all[img][kp]);
+      cam_idx.push_back(static_cast<int32_t>(img));
+      pt_idx.push_back(ids[kp]);
+      obs_xy.push_back(xy[0]);
+      obs_xy.push_back(xy[1]);
+    }
+  }
+}
+
+// Every ReprojectCost block that bundle_adjustment() (:1162-1244) hands to Ceres, in its order:
+// residuals [n_obs x 2], returns the HuberLoss(4) cost (:1184); *rmse = sqrt(cost / n_obs) as printed
+// at :1237-1238.
+template <class Point2fT, class Point3dT>
+double bundle_adjustment_residuals(const Context& c, const double intrinsic[4], const std::vector<double>& extrinsics6,
+                                   const std::vector<std::vector<int>>& correspond_struct_idx,
+                                   const std::vector<std::vector<Point2fT>>& key_points_for_all,
+                                   const std::vector<Point3dT>& structure, std::vector<double>& residuals,
+                                   double* rmse = nullptr, double huber_delta = 4.0) {
+  std::vector<int32_t> cam_idx, pt_idx;
+  std::vector<float> obs_xy;
+  enumerate_observations(correspond_struct_idx, key_points_for_all, cam_idx, pt_idx, obs_xy);
+  const double cost = reproject_residuals(c, intrinsic, extrinsics6, structure, cam_idx, pt_idx, obs_xy, residuals,
+                                          huber_delta);
+  if (rmse) *rmse = cam_idx.empty() ? 0.0 : std::sqrt(cost / static_cast<double>(cam_idx.size()));
   return cost;
 }
 
