@@ -135,7 +135,7 @@ cudaError_t launch_commit_rows(const uint8_t* desc, const int32_t* img_row0, con
 // ------------------------------------------------------------------------------- recheck
 // Rows the ratio-driven sweep of match_knn.cu (kPrune) could not decide: exact k = 2 search of the
 // query row against its whole train image on the CUDA cores (a few rows in 10^4 on unrelated images,
-// 0.5-2.5 % on the bundled datasets, where about half of the true matches have a fail range that
+// 0.3-3.5 % on the bundled datasets, where about half of the true matches have a fail range that
 // reaches into skipped columns).
 //   1. the list is counting-sorted by pair (recheck_hist / scan_counts / recheck_scatter), so that
 //      rows which read the same train image sit next to each other;

@@ -72,3 +72,18 @@ def test_property_lists_equal(seed, nq, nt, ratio, dup, noise, warp_rows, partne
     ok, _, _ = _lists_equal(q, t, ratio, warp_rows=warp_rows, partner=partner, cold_tiles=max(cold, 1),
                             seed_group=cold == 0, seed=seed)
     assert ok
+
+
+@pytest.mark.parametrize("name,rows", [("crazyhorse", None), ("desktop", 768), ("dog", 768)])
+def test_real_dataset_pairs_lists_equal(golden, name, rows):
+    """The rule on real SIFT descriptors (bundled datasets, first consecutive pair): same lists as the
+    exact table; the undecided rows are a fraction of the true matches."""
+    z = golden(name)
+    keys = sorted(k for k in z.files if k.startswith("desc"))
+    q, t = M.as_u8(z[keys[0]]), M.as_u8(z[keys[1]])
+    if rows is not None:
+        q = q[:rows]
+    for seed_group in (False, True):
+        ok, flagged, _ = _lists_equal(q, t, 0.6, warp_rows=32, partner="mixed", seed_group=seed_group)
+        assert ok
+        assert flagged.mean() < 0.10        # a third to three quarters of the true matches (0.9 - 9 % of the rows)
