@@ -11,6 +11,10 @@ kNN k=2 + Lowe ratio + min-distance gate exactly as match_features()
 Pairs are sharded over ranks in contiguous cost-balanced blocks (no data-path collective on
 results); total work is fixed by the config, so the scaling label is "strong".
 
+The calls ask for match lists only (no raw kNN rows), so the library runs its ratio-driven sweep
+(SFM_PRUNE_MODE=0 switches it off for an A/B run) -- lists, distances and min_dist are
+those of the exact search, which `self_check` verifies every run.
+
 Prints ONE JSON line (rank 0).  `value` = pairs/s with descriptors resident in HBM;
 `e2e` = pairs/s through the reference-facing call (host CV_32F descriptor matrices in,
 host DMatch lists out, copies inside the timed region).  With N > 1 ranks every image crosses
